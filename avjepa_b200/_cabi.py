@@ -1,0 +1,120 @@
+"""ctypes binding of ``libavjepa_sm100.so`` (the C ABI declared in ``include/avjepa_b200.h``).
+
+There is no CPU or PyTorch fallback: if the library is missing or a call fails the caller
+gets an exception.  Build the library with ``python -c 'import __graft_entry__ as g; g.build()'``
+or ``make -C avjepa_b200/csrc``.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libavjepa_sm100.so')
+
+F32, BF16 = 0, 1
+GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
+
+
+class RowMap(C.Structure):
+    _fields_ = [('rows_per_group', C.c_int32), ('group_stride', C.c_int32), ('row_offset', C.c_int32)]
+
+
+IDENTITY = RowMap(0, 0, 0)
+
+
+class Epilogue(C.Structure):
+    _fields_ = [
+        ('bias', C.c_void_p), ('residual', C.c_void_p), ('pos', C.c_void_p), ('pos_idx', C.c_void_p),
+        ('pos_rows', C.c_int32), ('act', C.c_int32),
+        ('pre_out', C.c_void_p), ('dact_aux', C.c_void_p),
+        ('accumulate', C.c_int32), ('out_dtype', C.c_int32),
+        ('out_map', RowMap),
+    ]
+
+
+class AdamWArgs(C.Structure):
+    _fields_ = [
+        ('p', C.c_void_p), ('g', C.c_void_p), ('m', C.c_void_p), ('v', C.c_void_p),
+        ('target', C.c_void_p), ('p_lp', C.c_void_p), ('target_lp', C.c_void_p),
+        ('n', C.c_int64),
+        ('lr', C.c_float), ('wd', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float), ('eps', C.c_float),
+        ('step', C.c_int32), ('ema_m', C.c_float), ('skip_update', C.c_int32), ('zero_grad', C.c_int32),
+        ('scale_ptr', C.c_void_p),
+    ]
+
+
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+# name -> (restype, argtypes); mirrors include/avjepa_b200.h one to one
+PROTOTYPES = {
+    'avj_version': (_i, []),
+    'avj_last_error_string': (C.c_char_p, []),
+    'avj_device_ok': (_i, []),
+    'avj_gemm': (_i, [_i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, C.POINTER(Epilogue), _vp]),
+    'avj_patchify': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    'avj_gather_rows_fwd': (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'avj_gather_rows_bwd': (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'avj_copy_rows': (_i, [_vp, _i, _i, RowMap, _vp, _i, _i, RowMap, _i, _i, _i, _vp]),
+    'avj_fill_mask_tokens': (_i, [_vp, _vp, _vp, _vp, _i, RowMap, _i, _i, _vp]),
+    'avj_colsum_ws_floats': (_i64, [_i, _i]),
+    'avj_colsum': (_i, [_vp, _i, _i, RowMap, _vp, _i, _i, _vp, _vp]),
+    'avj_layernorm_fwd': (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _f, _vp]),
+    'avj_layernorm_bwd_ws_floats': (_i64, [_i, _i]),
+    'avj_layernorm_bwd': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
+    'avj_attention_fwd': (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    'avj_attention_bwd_ws_floats': (_i64, [_i, _i, _i, _i]),
+    'avj_attention_bwd': (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    'avj_loss_ws_floats': (_i64, [_i64]),
+    'avj_loss_fwd_bwd': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _f, _i, _f, _f, _vp, _vp]),
+    'avj_reg_accumulate': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    'avj_reg_finish': (_i, [_vp, _vp, _i, _vp]),
+    'avj_adamw_ema_step': (_i, [C.POINTER(AdamWArgs), _vp]),
+    'avj_sumsq_ws_floats': (_i64, [_i64]),
+    'avj_sumsq': (_i, [_vp, _i64, _vp, _vp, _vp]),
+    'avj_clip_coef': (_i, [_vp, _f, _f, _vp, _vp]),
+    'avj_cast': (_i, [_vp, _vp, _i, _i64, _vp]),
+    'avj_memset_zero': (_i, [_vp, _i64, _vp]),
+}
+
+_lib = None
+
+
+class AvjError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library once; raise loudly if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AvjError(
+            f'{LIB_PATH} not found: the CUDA library is not built. Run '
+            f'`python -c "import __graft_entry__ as g; g.build()"` (or `make -C avjepa_b200/csrc`). '
+            f'There is no CPU fallback.')
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)      # AttributeError here means header and library disagree
+        fn.restype = res
+        fn.argtypes = args
+    if lib.avj_version() != 1:
+        raise AvjError(f'ABI version mismatch: library reports {lib.avj_version()}, binding expects 1')
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().avj_last_error_string()
+        raise AvjError(f'{what} failed (rc={rc}): {msg.decode() if msg else "?"}')
+
+
+# launch counter: bench.py reports how many of OUR kernels-launching calls ran in the timed region
+launch_count = 0
+
+
+def call(name, *args):
+    global launch_count
+    lib = load()
+    launch_count += 1
+    check(getattr(lib, name)(*args), name)

@@ -1,0 +1,74 @@
+// C-ABI dispatch for the compute-bound entry points (GEMM, attention): picks the tensor-core
+// kernel when the problem qualifies, the fp32-FMA check-mode kernel otherwise.  The choice can
+// be forced with AVJ_FORCE_SIMT=1 (debugging / A-B parity runs).
+#include "common.cuh"
+
+#include <stdlib.h>
+
+int avj_gemm_simt(int dtype, int layout, const void* A, const void* B, void* C, int M, int N, int K,
+                  int lda, int ldb, int ldc, const avj_epilogue& ep, cudaStream_t s);
+bool avj_gemm_umma_supported(int dtype, int layout, const void* A, const void* B, int M, int N, int K,
+                             int lda, int ldb, const avj_epilogue& ep);
+int avj_gemm_umma(int layout, const void* A, const void* B, void* C, int M, int N, int K,
+                  int lda, int ldb, int ldc, const avj_epilogue& ep, cudaStream_t s);
+int avj_attention_fwd_simt(int dtype, const void* qkv, void* out, float* lse, int B, int N, int H, int hd, float scale, cudaStream_t s);
+int avj_attention_bwd_simt(int dtype, const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                           float* ws, int B, int N, int H, int hd, float scale, cudaStream_t s);
+bool avj_attention_mma_supported(int dtype, int hd);
+int avj_attention_fwd_mma(const void* qkv, void* out, float* lse, int B, int N, int H, int hd, float scale, cudaStream_t s);
+int avj_attention_bwd_mma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                          float* ws, int B, int N, int H, int hd, float scale, cudaStream_t s);
+
+static bool force_simt() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("AVJ_FORCE_SIMT"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+static bool force_simt_attn() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("AVJ_FORCE_SIMT_ATTN"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1 || force_simt();
+}
+
+extern "C" int avj_gemm(int dtype, int layout, const void* A, const void* B, void* C,
+                        int M, int N, int K, int lda, int ldb, int ldc,
+                        const avj_epilogue* ep_in, void* stream) {
+  AVJ_CHECK(ep_in != nullptr, "avj_gemm: epilogue must not be NULL");
+  AVJ_CHECK(dtype == AVJ_F32 || dtype == AVJ_BF16, "avj_gemm: bad dtype %d", dtype);
+  AVJ_CHECK(N % 8 == 0 && ldc % 8 == 0, "avj_gemm: N and ldc must be multiples of 8 (N=%d ldc=%d)", N, ldc);
+  AVJ_CHECK(!(ep_in->accumulate && ep_in->out_dtype != AVJ_F32), "avj_gemm: accumulate needs an fp32 C");
+  if (M == 0 || N == 0) return 0;
+  avj_epilogue ep = *ep_in;
+  if (K == 0) {
+    AVJ_CHECK(ep.accumulate, "avj_gemm: K == 0 is only meaningful for accumulate epilogues");
+    return 0;
+  }
+  if (!force_simt() && avj_gemm_umma_supported(dtype, layout, A, B, M, N, K, lda, ldb, ep))
+    return avj_gemm_umma(layout, A, B, C, M, N, K, lda, ldb, ldc, ep, as_stream(stream));
+  return avj_gemm_simt(dtype, layout, A, B, C, M, N, K, lda, ldb, ldc, ep, as_stream(stream));
+}
+
+extern "C" int64_t avj_attention_bwd_ws_floats(int B, int N, int H, int hd) {
+  (void)hd;
+  return (int64_t)B * H * N;   // delta
+}
+
+extern "C" int avj_attention_fwd(int dtype, const void* qkv, void* out, float* lse,
+                                 int B, int N, int H, int hd, float scale, void* stream) {
+  AVJ_CHECK(hd > 0 && hd <= 128, "avj_attention_fwd: head_dim %d out of range (1..128)", hd);
+  if (B == 0 || N == 0) return 0;
+  if (!force_simt_attn() && avj_attention_mma_supported(dtype, hd))
+    return avj_attention_fwd_mma(qkv, out, lse, B, N, H, hd, scale, as_stream(stream));
+  return avj_attention_fwd_simt(dtype, qkv, out, lse, B, N, H, hd, scale, as_stream(stream));
+}
+
+extern "C" int avj_attention_bwd(int dtype, const void* qkv, const void* out, const void* dout,
+                                 const float* lse, void* dqkv, float* ws,
+                                 int B, int N, int H, int hd, float scale, void* stream) {
+  AVJ_CHECK(hd > 0 && hd <= 128, "avj_attention_bwd: head_dim %d out of range (1..128)", hd);
+  AVJ_CHECK(ws != nullptr, "avj_attention_bwd: workspace required");
+  if (B == 0 || N == 0) return 0;
+  if (!force_simt_attn() && avj_attention_mma_supported(dtype, hd))
+    return avj_attention_bwd_mma(qkv, out, dout, lse, dqkv, ws, B, N, H, hd, scale, as_stream(stream));
+  return avj_attention_bwd_simt(dtype, qkv, out, dout, lse, dqkv, ws, B, N, H, hd, scale, as_stream(stream));
+}

@@ -1,0 +1,209 @@
+// Shared helpers for the sm_100a kernels: error plumbing, dtype load/store, row maps.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/avjepa_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing (thread-local last error; no exceptions cross the C ABI) ----------
+void avj_set_error(const char* fmt, ...);
+
+#define AVJ_CHECK(cond, ...)                                                     \
+  do {                                                                           \
+    if (!(cond)) {                                                               \
+      avj_set_error(__VA_ARGS__);                                                \
+      return 1;                                                                  \
+    }                                                                            \
+  } while (0)
+
+#define AVJ_CUDA(expr)                                                           \
+  do {                                                                           \
+    cudaError_t e__ = (expr);                                                    \
+    if (e__ != cudaSuccess) {                                                    \
+      avj_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),     \
+                    __FILE__, __LINE__);                                         \
+      return 2;                                                                  \
+    }                                                                            \
+  } while (0)
+
+#define AVJ_LAUNCH_CHECK()                                                       \
+  do {                                                                           \
+    cudaError_t e__ = cudaGetLastError();                                        \
+    if (e__ != cudaSuccess) {                                                    \
+      avj_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), \
+                    __FILE__, __LINE__);                                         \
+      return 3;                                                                  \
+    }                                                                            \
+  } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int avj_num_sms();
+
+// ---- dtype helpers ------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void unpack_bf16x2(uint32_t u, float& lo, float& hi) {
+  __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
+  lo = __bfloat162float(t.x);
+  hi = __bfloat162float(t.y);
+}
+
+// Load / store 8 consecutive elements as floats (16 B for bf16, 32 B for fp32).
+template <typename T> __device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <> __device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8<bf16>(const bf16* p, float (&v)[8]) {
+  uint4 a = *reinterpret_cast<const uint4*>(p);
+  unpack_bf16x2(a.x, v[0], v[1]); unpack_bf16x2(a.y, v[2], v[3]);
+  unpack_bf16x2(a.z, v[4], v[5]); unpack_bf16x2(a.w, v[6], v[7]);
+}
+template <typename T> __device__ __forceinline__ void store8(T* p, const float (&v)[8]);
+template <> __device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void store8<bf16>(bf16* p, const float (&v)[8]) {
+  uint4 a;
+  a.x = pack_bf16x2(v[0], v[1]); a.y = pack_bf16x2(v[2], v[3]);
+  a.z = pack_bf16x2(v[4], v[5]); a.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = a;
+}
+
+// ---- row map -----------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int64_t map_row(const avj_rowmap& m, int64_t r) {
+  if (m.rows_per_group == 0) return r + m.row_offset;
+  return (r / m.rows_per_group) * (int64_t)m.group_stride + (r % m.rows_per_group) + m.row_offset;
+}
+
+// ---- math --------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum for blockDim.x <= 1024 (multiple of 32); `red` is >= 32 floats of smem.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (w == 0) t = warp_sum(t);
+  if (threadIdx.x == 0) red[0] = t;
+  __syncthreads();
+  return red[0];
+}
+
+// ---- shared GEMM epilogue (used by the SIMT check-mode GEMM and the tcgen05 GEMM) ----------
+// Applies the avj_epilogue to `NV` consecutive accumulator columns of logical row r starting at
+// column n0 (all in range: caller clips), and stores them.  NV must be a multiple of 4.
+template <typename TAct, int NV>
+__device__ __forceinline__ void epilogue_apply_store(const avj_epilogue& ep, void* C, int ldc, int N,
+                                                     int64_t r, int n0, float (&acc)[NV]) {
+  if (ep.bias) {
+#pragma unroll
+    for (int i = 0; i < NV; i += 4) {
+      float4 b = *reinterpret_cast<const float4*>(ep.bias + n0 + i);
+      acc[i] += b.x; acc[i + 1] += b.y; acc[i + 2] += b.z; acc[i + 3] += b.w;
+    }
+  }
+  if (ep.act == 1) {
+    if (ep.pre_out) {
+      TAct* pre = reinterpret_cast<TAct*>(ep.pre_out) + r * (int64_t)N + n0;
+#pragma unroll
+      for (int i = 0; i < NV; i += 8) {
+        float t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = acc[i + j];
+        store8<TAct>(pre + i, t);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = gelu_erf(acc[i]);
+  }
+  if (ep.dact_aux) {
+    const TAct* aux = reinterpret_cast<const TAct*>(ep.dact_aux) + r * (int64_t)N + n0;
+#pragma unroll
+    for (int i = 0; i < NV; i += 8) {
+      float t[8];
+      load8<TAct>(aux + i, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i + j] *= gelu_erf_grad(t[j]);
+    }
+  }
+  const int64_t pr = map_row(ep.out_map, r);
+  if (ep.residual) {
+    const float* res = ep.residual + pr * (int64_t)ldc + n0;
+#pragma unroll
+    for (int i = 0; i < NV; i += 4) {
+      float4 b = *reinterpret_cast<const float4*>(res + i);
+      acc[i] += b.x; acc[i + 1] += b.y; acc[i + 2] += b.z; acc[i + 3] += b.w;
+    }
+  }
+  if (ep.pos) {
+    const int64_t prow = ep.pos_idx ? ep.pos_idx[r] : (r % ep.pos_rows);
+    const float* pp = ep.pos + prow * (int64_t)N + n0;
+#pragma unroll
+    for (int i = 0; i < NV; i += 4) {
+      float4 b = *reinterpret_cast<const float4*>(pp + i);
+      acc[i] += b.x; acc[i + 1] += b.y; acc[i + 2] += b.z; acc[i + 3] += b.w;
+    }
+  }
+  if (ep.out_dtype == AVJ_F32) {
+    float* out = reinterpret_cast<float*>(C) + pr * (int64_t)ldc + n0;
+    if (ep.accumulate) {
+#pragma unroll
+      for (int i = 0; i < NV; i += 4) {
+        float4 b = *reinterpret_cast<const float4*>(out + i);
+        acc[i] += b.x; acc[i + 1] += b.y; acc[i + 2] += b.z; acc[i + 3] += b.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; i += 4)
+      *reinterpret_cast<float4*>(out + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+  } else {
+    bf16* out = reinterpret_cast<bf16*>(C) + pr * (int64_t)ldc + n0;
+#pragma unroll
+    for (int i = 0; i < NV; i += 8) {
+      float t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = acc[i + j];
+      store8<bf16>(out + i, t);
+    }
+  }
+}

@@ -1,0 +1,405 @@
+// K6 production GEMM for sm_100a: persistent, warp-specialised, TMA -> shared memory ->
+// tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> tcgen05.ld -> fused epilogue -> global.
+//
+//   warp 0      : TMA producer (one elected lane), 4-stage mbarrier ring
+//   warp 1      : TMEM allocator + MMA issuer (one elected lane), UMMA 128 x BN x 16
+//   warps 2..5  : epilogue; warp w owns TMEM lanes [32*(w%4), +32)
+//
+// CTA tile 128 x BN x 64 with BN in {64,128,192,256} chosen to divide N.  Two TMEM accumulator
+// buffers (2 x 256 columns) let the epilogue of tile i overlap the main loop of tile i+1.
+// Operand layouts: K-major (activations x weights^T, "NT"), MN-major B (dgrad, "NN") and
+// MN-major A and B (wgrad, "TN") -- the MN-major tiles are loaded as 64x64 TMA boxes and
+// described to the tensor core with the MN-major SWIZZLE_128B canonical layout, so no
+// transposed copy of any operand is ever materialised.  Weight gradients (tiny M x N, long K)
+// are split along K over CTAs and reduced with fp32 vector atomics into the gradient buffer.
+//
+// Roofline: tensor-bound.  Algorithmic FLOPs per launch = 2*M*N*K.
+#include "common.cuh"
+
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include <stdlib.h>
+
+#define UG_BM 128
+#define UG_BK 64
+#define UG_MAX_BN 256
+#define UG_STAGES 4
+#define UG_A_STAGE_BYTES (UG_BM * UG_BK * 2)        // 16 KB
+#define UG_B_STAGE_BYTES (UG_MAX_BN * UG_BK * 2)    // 32 KB
+#define UG_THREADS 192
+#define UG_SMEM_BYTES (UG_STAGES * (UG_A_STAGE_BYTES + UG_B_STAGE_BYTES) + 1024 + 256)
+
+struct UmmaParams {
+  int M, N, K, ldc;
+  int block_n;
+  int tiles_m, tiles_n;
+  int k_blocks;          // ceil(K / 64)
+  int split_k;           // >= 1
+  int kb_per_split;
+  int a_mn_major, b_mn_major;
+  uint32_t mn_lbo, mn_sbo, mn_kadv;   // MN-major descriptor fields / k-advance (16 B units)
+  void* C;
+  avj_epilogue ep;
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, SWIZZLE_128B, sm_100 version field = 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo16, uint32_t sbo16) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(lbo16 & 0x3FFF) << 16) | ((uint64_t)(sbo16 & 0x3FFF) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------
+template <typename TAct>
+__global__ void __launch_bounds__(UG_THREADS, 1)
+gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const UmmaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t smem_a = base;
+  const uint32_t smem_b = base + UG_STAGES * UG_A_STAGE_BYTES;
+  const uint32_t bars = smem_b + UG_STAGES * UG_B_STAGE_BYTES;
+  const uint32_t full_bar = bars;                       // [UG_STAGES]
+  const uint32_t empty_bar = bars + 8 * UG_STAGES;      // [UG_STAGES]
+  const uint32_t tfull_bar = bars + 16 * UG_STAGES;     // [2]
+  const uint32_t tempty_bar = tfull_bar + 16;           // [2]
+  const uint32_t tmem_slot = tempty_bar + 16;           // u32
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
+    for (int i = 0; i < UG_STAGES; ++i) { mbar_init(full_bar + 8 * i, 1); mbar_init(empty_bar + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + 8 * i, 1); mbar_init(tempty_bar + 8 * i, 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int n_units = p.tiles_m * p.tiles_n * p.split_k;
+  const uint32_t b_box_bytes = (uint32_t)p.block_n * UG_BK * 2;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int tile = u / p.split_k, ks = u % p.split_k;
+        const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          const uint32_t fb = full_bar + 8 * stage;
+          mbar_expect_tx(fb, UG_A_STAGE_BYTES + b_box_bytes);
+          const uint32_t sa = smem_a + stage * UG_A_STAGE_BYTES;
+          const uint32_t sb = smem_b + stage * UG_B_STAGE_BYTES;
+          if (!p.a_mn_major) {
+            tma_load_2d(sa, &tma_a, fb, kb * UG_BK, m_blk * UG_BM);
+          } else {
+            tma_load_2d(sa, &tma_a, fb, m_blk * UG_BM, kb * UG_BK);
+            tma_load_2d(sa + 8192, &tma_a, fb, m_blk * UG_BM + 64, kb * UG_BK);
+          }
+          if (!p.b_mn_major) {
+            tma_load_2d(sb, &tma_b, fb, kb * UG_BK, n_blk * p.block_n);
+          } else {
+            for (int j = 0; j < p.block_n / 64; ++j)
+              tma_load_2d(sb + j * 8192, &tma_b, fb, n_blk * p.block_n + j * 64, kb * UG_BK);
+          }
+          if (++stage == UG_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn_major << 15) |
+                             ((uint32_t)p.b_mn_major << 16) | ((uint32_t)(p.block_n >> 3) << 17) |
+                             ((uint32_t)(UG_BM >> 4) << 24);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int ks = u % p.split_k;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+        mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * UG_MAX_BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_a + stage * UG_A_STAGE_BYTES;
+          const uint32_t sb = smem_b + stage * UG_B_STAGE_BYTES;
+          const uint64_t adesc0 = p.a_mn_major ? make_desc(sa, p.mn_lbo, p.mn_sbo) : make_desc(sa, 1, 64);
+          const uint64_t bdesc0 = p.b_mn_major ? make_desc(sb, p.mn_lbo, p.mn_sbo) : make_desc(sb, 1, 64);
+          const uint32_t a_adv = p.a_mn_major ? p.mn_kadv : 2u;   // 16-byte units per UMMA_K=16
+          const uint32_t b_adv = p.b_mn_major ? p.mn_kadv : 2u;
+#pragma unroll
+          for (int k = 0; k < UG_BK / 16; ++k) {
+            tc_mma_bf16(tmem_d, adesc0 + (uint64_t)(k * a_adv), bdesc0 + (uint64_t)(k * b_adv), idesc,
+                        (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(empty_bar + 8 * stage);          // frees the smem stage when these MMAs retire
+          if (++stage == UG_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull_bar + 8 * acc);              // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue warps =================
+    const int q = warp & 3;                          // TMEM lane quarter this warp may touch
+    uint32_t acc = 0, acc_phase = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int tile = u / p.split_k;
+      const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      tc_fence_after();
+      const int64_t row = (int64_t)m_blk * UG_BM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * UG_MAX_BN;
+      for (int c = 0; c < p.block_n; c += 32) {
+        float v[32];
+        tmem_ld32(taddr + c, v);
+        const int n0 = n_blk * p.block_n + c;
+        if (row < p.M && n0 < p.N) {
+          if (p.split_k > 1) {
+            float* out = reinterpret_cast<float*>(p.C) + map_row(p.ep.out_map, row) * (int64_t)p.ldc + n0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) atomicAdd(reinterpret_cast<float4*>(out + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+          } else {
+            epilogue_apply_store<TAct, 32>(p.ep, p.C, p.ldc, p.N, row, n0, v);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host: tensor-map cache + launch
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; uint64_t inner, outer, ld; uint32_t box_inner, box_outer;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h = h * 1000003u ^ k.inner; h = h * 1000003u ^ k.outer; h = h * 1000003u ^ k.ld;
+    h = h * 1000003u ^ k.box_inner; h = h * 1000003u ^ k.box_outer;
+    return h;
+  }
+};
+
+// 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows, row pitch `ld` elements.
+static int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                          uint32_t box_outer, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return 0; }
+  }
+  PFN_encodeTiled enc = get_encode_fn();
+  AVJ_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AVJ_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%llu outer=%llu ld=%llu box=%ux%u", (int)r,
+            ptr, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner, box_outer);
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 8192) cache.clear();
+    cache[key] = *out;
+  }
+  return 0;
+}
+
+static int pick_block_n(int N) {
+  const int cands[4] = {256, 192, 128, 64};
+  for (int i = 0; i < 4; ++i) if (N % cands[i] == 0) return cands[i];
+  return 0;
+}
+
+static uint32_t env_u32(const char* name, uint32_t dflt) {
+  const char* s = getenv(name);
+  return s ? (uint32_t)strtoul(s, nullptr, 0) : dflt;
+}
+
+bool avj_gemm_umma_supported(int dtype, int layout, const void* A, const void* B, int M, int N, int K,
+                             int lda, int ldb, const avj_epilogue& ep) {
+  if (dtype != AVJ_BF16) return false;
+  if (M <= 0 || K <= 0 || pick_block_n(N) == 0) return false;
+  if ((lda % 8) || (ldb % 8)) return false;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return false;
+  if (layout == AVJ_GEMM_TN && (M % 8)) return false;
+  if (layout != AVJ_GEMM_NT && layout != AVJ_GEMM_NN && layout != AVJ_GEMM_TN) return false;
+  (void)ep;
+  return true;
+}
+
+int avj_gemm_umma(int layout, const void* A, const void* B, void* C, int M, int N, int K,
+                  int lda, int ldb, int ldc, const avj_epilogue& ep, cudaStream_t s) {
+  UmmaParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.C = C; p.ep = ep;
+  p.block_n = pick_block_n(N);
+  p.tiles_m = (M + UG_BM - 1) / UG_BM;
+  p.tiles_n = N / p.block_n;
+  p.k_blocks = (K + UG_BK - 1) / UG_BK;
+  p.a_mn_major = (layout == AVJ_GEMM_TN);
+  p.b_mn_major = (layout != AVJ_GEMM_NT);
+  // MN-major SWIZZLE_128B canonical layout: 64-element MN atoms 8192 B apart (one TMA box each),
+  // 8-row K groups 1024 B apart; one UMMA_K=16 step = 2 K groups = 2048 B.
+  static const uint32_t mn_lbo = env_u32("AVJ_UMMA_MN_LBO", 8192 / 16);
+  static const uint32_t mn_sbo = env_u32("AVJ_UMMA_MN_SBO", 1024 / 16);
+  static const uint32_t mn_kadv = env_u32("AVJ_UMMA_MN_KADV", 2048 / 16);
+  p.mn_lbo = mn_lbo; p.mn_sbo = mn_sbo; p.mn_kadv = mn_kadv;
+
+  const int sms = avj_num_sms();
+  const int tiles = p.tiles_m * p.tiles_n;
+  p.split_k = 1;
+  const bool pure_accumulate = ep.accumulate && ep.out_dtype == AVJ_F32 && !ep.bias && !ep.residual && !ep.pos &&
+                               !ep.act && !ep.dact_aux;
+  if (pure_accumulate && tiles < 2 * sms && p.k_blocks >= 8) {
+    int want = (2 * sms + tiles - 1) / tiles;
+    int max_split = p.k_blocks / 4;
+    if (want > max_split) want = max_split;
+    if (want < 1) want = 1;
+    p.split_k = want;
+  }
+  p.kb_per_split = (p.k_blocks + p.split_k - 1) / p.split_k;
+  p.split_k = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;   // drop empty splits
+
+  CUtensorMap ma, mb;
+  int rc;
+  if (!p.a_mn_major) rc = get_tensor_map(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, UG_BK, UG_BM, &ma);
+  else               rc = get_tensor_map(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, UG_BK, &ma);
+  if (rc) return rc;
+  if (!p.b_mn_major) rc = get_tensor_map(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, UG_BK, (uint32_t)p.block_n, &mb);
+  else               rc = get_tensor_map(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, UG_BK, &mb);
+  if (rc) return rc;
+
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_umma_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, UG_SMEM_BYTES);
+  });
+  AVJ_CHECK(attr_err == cudaSuccess, "cudaFuncSetAttribute(gemm_umma_kernel) failed: %s", cudaGetErrorString(attr_err));
+
+  const int units = tiles * p.split_k;
+  const int grid = units < sms ? units : sms;
+  gemm_umma_kernel<bf16><<<grid, UG_THREADS, UG_SMEM_BYTES, s>>>(ma, mb, p);
+  AVJ_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,252 @@
+// K5 LayerNorm forward/backward over the fp32 residual stream (HBM-bound).
+// One warp owns one row; the row lives in registers (float4 per lane, D <= 2048), statistics
+// are warp-shuffle reductions.  Algorithmic bytes/row: fwd 4D read + sizeof(y)*D write;
+// bwd sizeof(dy)*D + 4D (x) [+4D dres] read, 4D [+2D] write.
+#include "common.cuh"
+
+#define LN_WARPS 8
+#define LN_MAX_BLOCKS (148 * 2)
+
+template <typename TY, int NV4>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     TY* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                     int rows, int D, float eps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = D / 4;
+  for (int64_t r = (int64_t)blockIdx.x * LN_WARPS + warp; r < rows; r += (int64_t)gridDim.x * LN_WARPS) {
+    const float4* xr = reinterpret_cast<const float4*>(x + r * D);
+    float4 v[NV4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c = lane + i * 32;
+      v[i] = (c < nvec) ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+        q += a * a + b * b + cc * cc + d * d;
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[r] = mean;
+      if (rstd_out) rstd_out[r] = rstd;
+    }
+    TY* yr = y + r * D;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        float4 g = gamma ? reinterpret_cast<const float4*>(gamma)[c] : make_float4(1.f, 1.f, 1.f, 1.f);
+        float4 b = beta ? reinterpret_cast<const float4*>(beta)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float o0 = (v[i].x - mean) * rstd * g.x + b.x;
+        const float o1 = (v[i].y - mean) * rstd * g.y + b.y;
+        const float o2 = (v[i].z - mean) * rstd * g.z + b.z;
+        const float o3 = (v[i].w - mean) * rstd * g.w + b.w;
+        if (sizeof(TY) == 4) {
+          reinterpret_cast<float4*>(yr)[c] = make_float4(o0, o1, o2, o3);
+        } else {
+          uint2 o; o.x = pack_bf16x2(o0, o1); o.y = pack_bf16x2(o2, o3);
+          reinterpret_cast<uint2*>(yr)[c] = o;
+        }
+      }
+    }
+  }
+}
+
+template <typename TY>
+static int launch_ln_fwd(const float* x, const float* gamma, const float* beta, TY* y, float* mean, float* rstd,
+                         int rows, int D, float eps, cudaStream_t s) {
+  const int nv4 = (D / 4 + 31) / 32;
+  int grid = (rows + LN_WARPS - 1) / LN_WARPS;
+  const int cap = avj_num_sms() * 8;
+  if (grid > cap) grid = cap;
+#define LN_CASE(NV) case NV: layernorm_fwd_kernel<TY, NV><<<grid, LN_WARPS * 32, 0, s>>>(x, gamma, beta, y, mean, rstd, rows, D, eps); break;
+  switch (nv4) {
+    LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
+    LN_CASE(9) LN_CASE(10) LN_CASE(11) LN_CASE(12) LN_CASE(13) LN_CASE(14) LN_CASE(15) LN_CASE(16)
+    default: avj_set_error("avj_layernorm_fwd: D=%d too large (max 2048)", D); return 1;
+  }
+#undef LN_CASE
+  AVJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int avj_layernorm_fwd(const float* x, const float* gamma, const float* beta,
+                                 void* y, int y_dtype, float* mean, float* rstd,
+                                 int rows, int D, float eps, void* stream) {
+  AVJ_CHECK(D % 4 == 0 && D > 0, "avj_layernorm_fwd: D must be a positive multiple of 4");
+  if (rows == 0) return 0;
+  if (y_dtype == AVJ_BF16) return launch_ln_fwd<bf16>(x, gamma, beta, (bf16*)y, mean, rstd, rows, D, eps, as_stream(stream));
+  return launch_ln_fwd<float>(x, gamma, beta, (float*)y, mean, rstd, rows, D, eps, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------
+extern "C" int64_t avj_layernorm_bwd_ws_floats(int rows, int D) {
+  (void)rows;
+  return (int64_t)LN_MAX_BLOCKS * 2 * D;
+}
+
+template <typename TDY>
+__device__ __forceinline__ float4 load4_as_f32(const TDY* p, int c);
+template <>
+__device__ __forceinline__ float4 load4_as_f32<float>(const float* p, int c) {
+  return reinterpret_cast<const float4*>(p)[c];
+}
+template <>
+__device__ __forceinline__ float4 load4_as_f32<bf16>(const bf16* p, int c) {
+  const uint2 u = reinterpret_cast<const uint2*>(p)[c];
+  float4 f;
+  unpack_bf16x2(u.x, f.x, f.y);
+  unpack_bf16x2(u.y, f.z, f.w);
+  return f;
+}
+
+template <typename TDY, typename TLP, int NV4>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
+                     float* __restrict__ dx, TLP* __restrict__ dx_lp, float* __restrict__ ws, int want_dgamma,
+                     int rows, int D) {
+  extern __shared__ float sm[];   // [LN_WARPS][2][D] partials, only when want_dgamma
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = D / 4;
+  float4 ag[NV4], ab[NV4];
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) { ag[i] = make_float4(0.f, 0.f, 0.f, 0.f); ab[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+
+  for (int64_t r = (int64_t)blockIdx.x * LN_WARPS + warp; r < rows; r += (int64_t)gridDim.x * LN_WARPS) {
+    const float mu = mean[r], rs = rstd[r];
+    const float4* xr = reinterpret_cast<const float4*>(x + r * D);
+    const TDY* dyr = dy + r * D;
+    float4 xh[NV4], g[NV4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        const float4 xv = xr[c];
+        const float4 d = load4_as_f32<TDY>(dyr, c);
+        const float4 gm = gamma ? reinterpret_cast<const float4*>(gamma)[c] : make_float4(1.f, 1.f, 1.f, 1.f);
+        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        g[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+        s1 += g[i].x + g[i].y + g[i].z + g[i].w;
+        s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
+        ag[i].x += d.x * xh[i].x; ag[i].y += d.y * xh[i].y; ag[i].z += d.z * xh[i].z; ag[i].w += d.w * xh[i].w;
+        ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+      } else {
+        xh[i] = make_float4(0.f, 0.f, 0.f, 0.f); g[i] = xh[i];
+      }
+    }
+    const float m1 = warp_sum(s1) / (float)D;
+    const float m2 = warp_sum(s2) / (float)D;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        float4 o = make_float4(rs * (g[i].x - m1 - xh[i].x * m2), rs * (g[i].y - m1 - xh[i].y * m2),
+                               rs * (g[i].z - m1 - xh[i].z * m2), rs * (g[i].w - m1 - xh[i].w * m2));
+        if (dres) {
+          const float4 dr = reinterpret_cast<const float4*>(dres + r * D)[c];
+          o.x += dr.x; o.y += dr.y; o.z += dr.z; o.w += dr.w;
+        }
+        reinterpret_cast<float4*>(dx + r * D)[c] = o;
+        if (dx_lp) {
+          if (sizeof(TLP) == 4) {
+            reinterpret_cast<float4*>(dx_lp + r * D)[c] = o;
+          } else {
+            uint2 u; u.x = pack_bf16x2(o.x, o.y); u.y = pack_bf16x2(o.z, o.w);
+            reinterpret_cast<uint2*>(dx_lp + r * D)[c] = u;
+          }
+        }
+      }
+    }
+  }
+
+  if (want_dgamma) {
+    float* sg = sm + (size_t)warp * 2 * D;
+    float* sb = sg + D;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        reinterpret_cast<float4*>(sg)[c] = ag[i];
+        reinterpret_cast<float4*>(sb)[c] = ab[i];
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < LN_WARPS; ++w) t += sm[(size_t)w * 2 * D + c];
+      ws[(size_t)blockIdx.x * 2 * D + c] = t;
+    }
+  }
+}
+
+__global__ void layernorm_bwd_final_kernel(const float* __restrict__ ws, int nblocks, int D,
+                                           float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= 2 * D) return;
+  float t = 0.f;
+  for (int b = 0; b < nblocks; ++b) t += ws[(size_t)b * 2 * D + c];
+  if (c < D) { if (dgamma) dgamma[c] += t; }
+  else { if (dbeta) dbeta[c - D] += t; }
+}
+
+template <typename TDY, typename TLP>
+static int launch_ln_bwd(const TDY* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                         const float* dres, float* dx, TLP* dx_lp, float* dgamma, float* dbeta, float* ws,
+                         int rows, int D, cudaStream_t s) {
+  const int nv4 = (D / 4 + 31) / 32;
+  int grid = (rows + LN_WARPS - 1) / LN_WARPS;
+  if (grid > LN_MAX_BLOCKS) grid = LN_MAX_BLOCKS;
+  const int want = (dgamma != nullptr || dbeta != nullptr) ? 1 : 0;
+  const size_t smem = want ? (size_t)LN_WARPS * 2 * D * sizeof(float) : 0;
+#define LNB_CASE(NV)                                                                                          \
+  case NV: {                                                                                                  \
+    auto k = layernorm_bwd_kernel<TDY, TLP, NV>;                                                              \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+    k<<<grid, LN_WARPS * 32, smem, s>>>(dy, x, gamma, mean, rstd, dres, dx, dx_lp, ws, want, rows, D);          \
+  } break;
+  switch (nv4) {
+    LNB_CASE(1) LNB_CASE(2) LNB_CASE(3) LNB_CASE(4) LNB_CASE(5) LNB_CASE(6) LNB_CASE(7) LNB_CASE(8)
+    LNB_CASE(9) LNB_CASE(10) LNB_CASE(11) LNB_CASE(12) LNB_CASE(13) LNB_CASE(14) LNB_CASE(15) LNB_CASE(16)
+    default: avj_set_error("avj_layernorm_bwd: D=%d too large (max 2048)", D); return 1;
+  }
+#undef LNB_CASE
+  AVJ_LAUNCH_CHECK();
+  if (want) {
+    layernorm_bwd_final_kernel<<<(2 * D + 127) / 128, 128, 0, s>>>(ws, grid, D, dgamma, dbeta);
+    AVJ_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int avj_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma,
+                                 const float* mean, const float* rstd, const float* dres_in,
+                                 float* dx_out, void* dx_lp, int lp_dtype,
+                                 float* dgamma, float* dbeta, float* ws,
+                                 int rows, int D, void* stream) {
+  AVJ_CHECK(D % 4 == 0 && D > 0, "avj_layernorm_bwd: D must be a positive multiple of 4");
+  AVJ_CHECK(!(dgamma || dbeta) || ws, "avj_layernorm_bwd: workspace required for dgamma/dbeta");
+  if (rows == 0) return 0;
+  cudaStream_t s = as_stream(stream);
+  if (dy_dtype == AVJ_BF16) {
+    if (dx_lp && lp_dtype == AVJ_F32)
+      return launch_ln_bwd<bf16, float>((const bf16*)dy, x, gamma, mean, rstd, dres_in, dx_out, (float*)dx_lp, dgamma, dbeta, ws, rows, D, s);
+    return launch_ln_bwd<bf16, bf16>((const bf16*)dy, x, gamma, mean, rstd, dres_in, dx_out, (bf16*)dx_lp, dgamma, dbeta, ws, rows, D, s);
+  }
+  if (dx_lp && lp_dtype == AVJ_BF16)
+    return launch_ln_bwd<float, bf16>((const float*)dy, x, gamma, mean, rstd, dres_in, dx_out, (bf16*)dx_lp, dgamma, dbeta, ws, rows, D, s);
+  return launch_ln_bwd<float, float>((const float*)dy, x, gamma, mean, rstd, dres_in, dx_out, (float*)dx_lp, dgamma, dbeta, ws, rows, D, s);
+}

@@ -1,0 +1,353 @@
+"""Device engine: raw-pointer launches of the C-ABI kernels and the explicit forward/backward
+schedule of a pre-LN transformer stack.
+
+PyTorch is used here only for device memory (``torch.empty``), the current CUDA stream and
+the tensors handed back to the caller; every arithmetic step is a kernel of
+``libavjepa_sm100.so``.  Buffers inside one forward/backward are carved out of two byte
+arenas by integer pointer arithmetic (no per-op tensor objects):
+
+* the *saved* arena of a :class:`StackRun` holds every activation the backward needs
+  (per layer: x, LN stats, LN outputs, qkv, attention output + LSE, pre/post-GELU), laid out
+  layer-major so one ``torch.empty`` covers the whole stack;
+* the *scratch* arena is reused stream-ordered for temporaries (gradients flowing between
+  kernels, reduction workspaces).
+
+Residual stream and its gradient are fp32; GEMM/attention operands are the compute dtype
+(bf16 in production, fp32 in check mode).
+"""
+import ctypes as C
+
+import torch
+
+from avjepa_b200 import _cabi
+from avjepa_b200._cabi import BF16, F32, GEMM_NN, GEMM_NT, GEMM_TN, Epilogue, RowMap
+
+
+def _align(n, a=256):
+    return (n + a - 1) // a * a
+
+
+class Mode(object):
+    """Compute dtype of GEMM/attention operands."""
+
+    def __init__(self, code):
+        self.code = code
+        self.torch_dtype = torch.bfloat16 if code == BF16 else torch.float32
+        self.size = 2 if code == BF16 else 4
+
+    @staticmethod
+    def current():
+        """bf16 under ``torch.autocast('cuda', dtype=bfloat16)`` (what the reference train loop
+        enters, app/avjepa/train.py:502), fp32 check mode otherwise."""
+        if torch.is_autocast_enabled('cuda') and torch.get_autocast_dtype('cuda') == torch.bfloat16:
+            return MODE_BF16
+        return MODE_F32
+
+
+MODE_F32 = Mode(F32)
+MODE_BF16 = Mode(BF16)
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(t, what):
+    if not t.is_cuda:
+        raise _cabi.AvjError(f'{what}: expected a CUDA tensor (device={t.device}); avjepa_b200 has no CPU path')
+
+
+class Arena(object):
+    """Byte arena over one torch allocation; hands out raw device pointers."""
+
+    def __init__(self, nbytes, device):
+        self.nbytes = int(nbytes)
+        self.buf = torch.empty(max(self.nbytes, 256) + 256, dtype=torch.uint8, device=device)
+        self.base = _align(self.buf.data_ptr())
+        self.off = 0
+
+    def alloc(self, nbytes):
+        p = self.base + self.off
+        self.off += _align(int(nbytes))
+        if self.off > self.nbytes + 256:
+            raise _cabi.AvjError(f'arena overflow: need {self.off} of {self.nbytes} bytes')
+        return p
+
+
+class _Scratch(object):
+    """Per-device reusable scratch arena (stream-ordered reuse on the current stream)."""
+
+    def __init__(self):
+        self.arenas = {}
+
+    def get(self, nbytes, device):
+        key = (device.index, torch.cuda.current_stream().cuda_stream)
+        a = self.arenas.get(key)
+        if a is None or a.nbytes < nbytes:
+            a = Arena(int(nbytes * 1.25) + (1 << 20), device)
+            self.arenas[key] = a
+        a.off = 0
+        return a
+
+
+SCRATCH = _Scratch()
+
+
+# ----------------------------------------------------------------------------------------------
+# thin launch wrappers (all pointers are ints or None)
+# ----------------------------------------------------------------------------------------------
+def rowmap(rows_per_group=0, group_stride=0, row_offset=0):
+    return RowMap(int(rows_per_group), int(group_stride), int(row_offset))
+
+
+def gemm(mode, layout, A, B_, Cp, M, N, K, lda, ldb, ldc, out_dtype, bias=None, residual=None, pos=None,
+         pos_idx=None, pos_rows=0, act=0, pre_out=None, dact_aux=None, accumulate=0, out_map=None):
+    ep = Epilogue(bias, residual, pos, pos_idx, int(pos_rows), int(act), pre_out, dact_aux, int(accumulate),
+                  int(out_dtype), out_map if out_map is not None else _cabi.IDENTITY)
+    _cabi.call('avj_gemm', mode.code, layout, A, B_, Cp, int(M), int(N), int(K), int(lda), int(ldb), int(ldc),
+               C.byref(ep), stream())
+
+
+def layernorm_fwd(x, gamma, beta, y, y_dtype, mean, rstd, rows, D, eps):
+    _cabi.call('avj_layernorm_fwd', x, gamma, beta, y, y_dtype, mean, rstd, int(rows), int(D), float(eps), stream())
+
+
+def layernorm_bwd(dy, dy_dtype, x, gamma, mean, rstd, dres, dx, dx_lp, lp_dtype, dgamma, dbeta, ws, rows, D):
+    _cabi.call('avj_layernorm_bwd', dy, dy_dtype, x, gamma, mean, rstd, dres, dx, dx_lp, lp_dtype, dgamma, dbeta, ws,
+               int(rows), int(D), stream())
+
+
+def colsum(inp, in_dtype, ld, rmap, out, rows, D, ws):
+    _cabi.call('avj_colsum', inp, in_dtype, int(ld), rmap, out, int(rows), int(D), ws, stream())
+
+
+def copy_rows(inp, in_dtype, ld_in, imap, out, out_dtype, ld_out, omap, rows, D, accumulate=0):
+    _cabi.call('avj_copy_rows', inp, in_dtype, int(ld_in), imap, out, out_dtype, int(ld_out), omap, int(rows), int(D),
+               int(accumulate), stream())
+
+
+def memset0(ptr, nbytes):
+    _cabi.call('avj_memset_zero', ptr, int(nbytes), stream())
+
+
+# ----------------------------------------------------------------------------------------------
+# parameter views
+# ----------------------------------------------------------------------------------------------
+class LinearW(object):
+    """Pointers for one nn.Linear: weight in compute dtype, fp32 bias, fp32 grad buffers."""
+    __slots__ = ('w', 'b', 'gw', 'gb', 'out_f', 'in_f')
+
+    def __init__(self, lin, shadows, mode, want_grad):
+        self.out_f, self.in_f = lin.weight.shape
+        self.w = shadows.weight_ptr(lin.weight, mode)
+        self.b = lin.bias.data_ptr() if lin.bias is not None else None
+        self.gw = grad_ptr(lin.weight) if want_grad else None
+        self.gb = grad_ptr(lin.bias) if (want_grad and lin.bias is not None) else None
+
+
+class NormW(object):
+    __slots__ = ('w', 'b', 'gw', 'gb', 'eps')
+
+    def __init__(self, ln, want_grad):
+        self.w = ln.weight.data_ptr()
+        self.b = ln.bias.data_ptr()
+        self.eps = ln.eps
+        self.gw = grad_ptr(ln.weight) if want_grad else None
+        self.gb = grad_ptr(ln.bias) if want_grad else None
+
+
+class BlockW(object):
+    __slots__ = ('n1', 'qkv', 'proj', 'n2', 'fc1', 'fc2')
+
+    def __init__(self, blk, shadows, mode, want_grad):
+        self.n1 = NormW(blk.norm1, want_grad)
+        self.qkv = LinearW(blk.attn.qkv, shadows, mode, want_grad)
+        self.proj = LinearW(blk.attn.proj, shadows, mode, want_grad)
+        self.n2 = NormW(blk.norm2, want_grad)
+        self.fc1 = LinearW(blk.mlp.fc1, shadows, mode, want_grad)
+        self.fc2 = LinearW(blk.mlp.fc2, shadows, mode, want_grad)
+
+
+def grad_ptr(p):
+    """fp32 gradient buffer of a parameter, created zero-filled on first use.  Backward kernels
+    ACCUMULATE straight into it (weight-gradient GEMMs with a `C +=` epilogue), so no
+    per-parameter gradient temporaries exist."""
+    if not p.requires_grad:
+        return None
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    return p.grad.data_ptr()
+
+
+class Shadows(object):
+    """Compute-dtype copies of the 2-D+ weights of one module tree.
+
+    In fp32 mode the parameter itself is used.  In bf16 mode each weight has a bf16 shadow that
+    is refreshed (one cast kernel) whenever the parameter's version counter or storage changed;
+    the fused optimizer (:mod:`avjepa_b200.optim`) refreshes shadows itself inside the AdamW
+    kernel and marks them clean, so the steady-state step issues no cast kernels at all.
+    """
+
+    def __init__(self):
+        self.entries = {}     # id(param) -> [version, data_ptr, bf16 tensor]
+
+    def weight_ptr(self, p, mode):
+        if mode.code == F32:
+            return p.data_ptr()
+        e = self.entries.get(id(p))
+        if e is None:
+            e = [None, None, torch.empty(p.shape, dtype=torch.bfloat16, device=p.device)]
+            self.entries[id(p)] = e
+        if e[0] != p._version or e[1] != p.data_ptr():
+            _cabi.call('avj_cast', p.data_ptr(), e[2].data_ptr(), BF16, p.numel(), stream())
+            e[0], e[1] = p._version, p.data_ptr()
+        return e[2].data_ptr()
+
+    def adopt(self, p, shadow_tensor):
+        """Register an externally maintained shadow (a view into the optimizer's flat bf16 buffer)."""
+        self.entries[id(p)] = [p._version, p.data_ptr(), shadow_tensor]
+
+    def mark_clean(self, p):
+        e = self.entries.get(id(p))
+        if e is not None:
+            e[0], e[1] = p._version, p.data_ptr()
+
+
+# ----------------------------------------------------------------------------------------------
+# transformer stack
+# ----------------------------------------------------------------------------------------------
+class StackRun(object):
+    """One forward (and optionally backward) of L pre-LN blocks + final LayerNorm over a token
+    matrix [B*N, D].  Restates Block.forward / Attention.forward / MLP.forward of the reference
+    (src/models/utils/modules.py:114-120, :61-78, :30-36) as an explicit kernel schedule."""
+
+    def __init__(self, B, N, D, heads, depth, mode, save, device, hidden=None):
+        self.B, self.N, self.D, self.H, self.L = B, N, D, heads, depth
+        self.R = B * N
+        self.hd = D // heads
+        self.Hd = hidden if hidden is not None else 4 * D
+        self.mode, self.save, self.device = mode, save, device
+        R, s = self.R, mode.size
+        # per-layer saved layout (byte offsets)
+        o, lay = 0, {}
+        for name, nbytes in (('x', R * D * 4), ('mean1', R * 4), ('rstd1', R * 4), ('h1', R * D * s),
+                             ('qkv', R * 3 * D * s), ('o', R * D * s), ('lse', B * heads * N * 4),
+                             ('x1', R * D * 4), ('mean2', R * 4), ('rstd2', R * 4), ('h2', R * D * s),
+                             ('pre', R * self.Hd * s), ('act', R * self.Hd * s)):
+            lay[name] = o
+            o += _align(nbytes)
+        self.lay, self.layer_bytes = lay, o
+        n_layers_stored = depth if save else 1
+        tail = _align(R * D * 4) + 2 * _align(R * 4)            # x_L, final mean, rstd
+        self.arena = Arena(n_layers_stored * o + tail + 4096, device)
+        self.layer_base = [self.arena.alloc(o) for _ in range(n_layers_stored)]
+        self.x_final = self.arena.alloc(R * D * 4)
+        self.mean_f = self.arena.alloc(R * 4)
+        self.rstd_f = self.arena.alloc(R * 4)
+
+    # -- addressing ------------------------------------------------------------------------
+    def slot(self, layer, name):
+        base = self.layer_base[layer if self.save else 0]
+        return base + self.lay[name]
+
+    def x_in(self, layer):
+        """Input residual stream of `layer` (layer == L -> output of the last block).  Without
+        saving, the stream ping-pongs between two buffers."""
+        if self.save:
+            return self.slot(layer, 'x') if layer < self.L else self.x_final
+        return (self.slot(0, 'x'), self.x_final)[layer % 2]
+
+    def x_out(self, layer):
+        return self.x_in(layer + 1)
+
+    # -- forward ---------------------------------------------------------------------------
+    def forward_layer(self, i, w):
+        """x_{i+1} = Block_i(x_i): LN1 -> qkv -> attention -> proj(+x) -> LN2 -> fc1/GELU -> fc2(+x1)."""
+        m, R, D, Hd, cd = self.mode, self.R, self.D, self.Hd, self.mode.code
+        scale = float(self.hd ** -0.5)
+        x, x1, xo = self.x_in(i), self.slot(i, 'x1'), self.x_out(i)
+        layernorm_fwd(x, w.n1.w, w.n1.b, self.slot(i, 'h1'), cd, self.slot(i, 'mean1'), self.slot(i, 'rstd1'), R, D, w.n1.eps)
+        gemm(m, GEMM_NT, self.slot(i, 'h1'), w.qkv.w, self.slot(i, 'qkv'), R, 3 * D, D, D, D, 3 * D, cd, bias=w.qkv.b)
+        _cabi.call('avj_attention_fwd', cd, self.slot(i, 'qkv'), self.slot(i, 'o'), self.slot(i, 'lse'),
+                   self.B, self.N, self.H, self.hd, scale, stream())
+        gemm(m, GEMM_NT, self.slot(i, 'o'), w.proj.w, x1, R, D, D, D, D, D, F32, bias=w.proj.b, residual=x)
+        layernorm_fwd(x1, w.n2.w, w.n2.b, self.slot(i, 'h2'), cd, self.slot(i, 'mean2'), self.slot(i, 'rstd2'), R, D, w.n2.eps)
+        gemm(m, GEMM_NT, self.slot(i, 'h2'), w.fc1.w, self.slot(i, 'act'), R, Hd, D, D, D, Hd, cd, bias=w.fc1.b,
+             act=1, pre_out=self.slot(i, 'pre') if self.save else None)
+        gemm(m, GEMM_NT, self.slot(i, 'act'), w.fc2.w, xo, R, D, Hd, Hd, Hd, D, F32, bias=w.fc2.b, residual=x1)
+
+    def forward(self, blocks, norm, out_ptr, out_dtype):
+        """blocks: list[BlockW]; norm: NormW or None.  Writes LN(x_L) to out_ptr."""
+        R, D = self.R, self.D
+        for i, w in enumerate(blocks):
+            self.forward_layer(i, w)
+        self.x_last = self.x_in(self.L)
+        if norm is not None:
+            layernorm_fwd(self.x_last, norm.w, norm.b, out_ptr, out_dtype, self.mean_f, self.rstd_f, R, D, norm.eps)
+        else:
+            copy_rows(self.x_last, F32, D, _cabi.IDENTITY, out_ptr, out_dtype, D, _cabi.IDENTITY, R, D)
+
+    # -- backward --------------------------------------------------------------------------
+    def scratch_bytes(self):
+        R, D, Hd, s = self.R, self.D, self.Hd, self.mode.size
+        per = 2 * _align(R * D * 4) + _align(R * D * s) + _align(R * Hd * s) + _align(R * 3 * D * s) + 2 * _align(R * D * s)
+        ws = max(_cabi.load().avj_layernorm_bwd_ws_floats(R, D), _cabi.load().avj_colsum_ws_floats(R, 3 * max(D, Hd)),
+                 _cabi.load().avj_attention_bwd_ws_floats(self.B, self.N, self.H, self.hd)) * 4
+        return per + _align(ws) + (1 << 16)
+
+    def backward(self, blocks, norm, dy_ptr, dy_dtype, sc):
+        """dy: gradient wrt LN(x_L) output, [R, D] contiguous in dy_dtype.  `sc` is a scratch
+        Arena with at least scratch_bytes().  Returns the pointer of d x_0 (fp32, in scratch)."""
+        assert self.save, 'backward needs a forward run with save=True'
+        m, R, D, Hd, cd, s = self.mode, self.R, self.D, self.Hd, self.mode.code, self.mode.size
+        scale = float(self.hd ** -0.5)
+        dxa = sc.alloc(R * D * 4)          # fp32 residual-gradient ping
+        dxb = sc.alloc(R * D * 4)          # pong
+        dx_lp = sc.alloc(R * D * s)        # compute-dtype copy feeding the GEMMs
+        d_hid = sc.alloc(R * Hd * s)       # d pre-GELU
+        d_qkv = sc.alloc(R * 3 * D * s)
+        d_h = sc.alloc(R * D * s)          # d LN-output (h2 / h1)
+        d_o = sc.alloc(R * D * s)
+        lib = _cabi.load()
+        ws = sc.alloc(4 * max(lib.avj_layernorm_bwd_ws_floats(R, D), lib.avj_colsum_ws_floats(R, 3 * max(D, Hd)),
+                              lib.avj_attention_bwd_ws_floats(self.B, self.N, self.H, self.hd)))
+        cur, nxt = dxa, dxb
+        if norm is not None:
+            layernorm_bwd(dy_ptr, dy_dtype, self.x_in(self.L), norm.w, self.mean_f, self.rstd_f, None, cur, dx_lp, cd,
+                          norm.gw, norm.gb, ws, R, D)
+        else:
+            copy_rows(dy_ptr, dy_dtype, D, _cabi.IDENTITY, cur, F32, D, _cabi.IDENTITY, R, D)
+            copy_rows(dy_ptr, dy_dtype, D, _cabi.IDENTITY, dx_lp, cd, D, _cabi.IDENTITY, R, D)
+        for i in reversed(range(self.L)):
+            w = blocks[i]
+            # ---- MLP: x2 = x1 + fc2(gelu(fc1(LN2(x1))))
+            if w.fc2.gb is not None:
+                colsum(dx_lp, cd, D, _cabi.IDENTITY, w.fc2.gb, R, D, ws)
+            if w.fc2.gw is not None:
+                gemm(m, GEMM_TN, dx_lp, self.slot(i, 'act'), w.fc2.gw, D, Hd, R, D, Hd, Hd, F32, accumulate=1)
+            gemm(m, GEMM_NN, dx_lp, w.fc2.w, d_hid, R, Hd, D, D, Hd, Hd, cd, dact_aux=self.slot(i, 'pre'))
+            if w.fc1.gb is not None:
+                colsum(d_hid, cd, Hd, _cabi.IDENTITY, w.fc1.gb, R, Hd, ws)
+            if w.fc1.gw is not None:
+                gemm(m, GEMM_TN, d_hid, self.slot(i, 'h2'), w.fc1.gw, Hd, D, R, Hd, D, D, F32, accumulate=1)
+            gemm(m, GEMM_NN, d_hid, w.fc1.w, d_h, R, D, Hd, Hd, D, D, cd)
+            layernorm_bwd(d_h, cd, self.slot(i, 'x1'), w.n2.w, self.slot(i, 'mean2'), self.slot(i, 'rstd2'), cur, nxt, dx_lp, cd,
+                          w.n2.gw, w.n2.gb, ws, R, D)
+            cur, nxt = nxt, cur
+            # ---- attention: x1 = x + proj(attn(qkv(LN1(x))))
+            if w.proj.gb is not None:
+                colsum(dx_lp, cd, D, _cabi.IDENTITY, w.proj.gb, R, D, ws)
+            if w.proj.gw is not None:
+                gemm(m, GEMM_TN, dx_lp, self.slot(i, 'o'), w.proj.gw, D, D, R, D, D, D, F32, accumulate=1)
+            gemm(m, GEMM_NN, dx_lp, w.proj.w, d_o, R, D, D, D, D, D, cd)
+            _cabi.call('avj_attention_bwd', cd, self.slot(i, 'qkv'), self.slot(i, 'o'), d_o, self.slot(i, 'lse'), d_qkv, ws,
+                       self.B, self.N, self.H, self.hd, scale, stream())
+            if w.qkv.gb is not None:
+                colsum(d_qkv, cd, 3 * D, _cabi.IDENTITY, w.qkv.gb, R, 3 * D, ws)
+            if w.qkv.gw is not None:
+                gemm(m, GEMM_TN, d_qkv, self.slot(i, 'h1'), w.qkv.gw, 3 * D, D, R, 3 * D, D, D, F32, accumulate=1)
+            gemm(m, GEMM_NN, d_qkv, w.qkv.w, d_h, R, D, 3 * D, 3 * D, D, D, cd)
+            layernorm_bwd(d_h, cd, self.slot(i, 'x'), w.n1.w, self.slot(i, 'mean1'), self.slot(i, 'rstd1'), cur, nxt, dx_lp, cd,
+                          w.n1.gw, w.n1.gb, ws, R, D)
+            cur, nxt = nxt, cur
+        return cur

@@ -1,0 +1,187 @@
+/*
+ * avjepa_b200.h -- C ABI of libavjepa_sm100.so, the sm_100a kernels behind the AV-JEPA
+ * masked encoder/predictor training step.
+ *
+ * The reference (johnshizhu/AVJEPA) is pure Python/PyTorch and has no FFI of its own; the
+ * drop-in boundary is its Python module API.  This header is the
+ * boundary UNDER that API: each entry point names the reference call site (file:line,
+ * relative to the reference root) whose device work it replaces.  Callers own every buffer
+ * and pass raw device pointers, sizes and a cudaStream_t; no torch types cross this line.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; avj_last_error_string()
+ *     describes the last failure on the calling thread.  Nothing throws.
+ *   - all matrices are row-major; `ld*` are leading dimensions in ELEMENTS.
+ *   - dtype codes: AVJ_F32 (fp32 "check mode": SIMT kernels, 1e-4 parity) and
+ *     AVJ_BF16 (production: tcgen05/TMEM/TMA tensor-core kernels, fp32 accumulate).
+ *   - `stream` is a cudaStream_t passed as void*.
+ *   - a "row map" sends logical row r to physical row
+ *         (r / rows_per_group) * group_stride + (r % rows_per_group) + row_offset;
+ *     rows_per_group == 0 means identity.  It lets kernels read/write the concatenated
+ *     [ctx_v | tgt_v | ctx_a | tgt_a] token layouts in place (no torch.cat copies).
+ */
+#ifndef AVJEPA_B200_H_
+#define AVJEPA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVJ_ABI_VERSION 1
+
+enum { AVJ_F32 = 0, AVJ_BF16 = 1 };
+
+/* GEMM operand layouts: which index is contiguous in memory. */
+enum {
+  AVJ_GEMM_NT = 0, /* C[M,N] = A[M,K] . B[N,K]^T   (fprop:  y = x W^T)          */
+  AVJ_GEMM_NN = 1, /* C[M,N] = A[M,K] . B[K,N]     (dgrad:  dx = dy W)          */
+  AVJ_GEMM_TN = 2  /* C[M,N] = A[K,M]^T . B[K,N]   (wgrad:  dW = dy^T x)        */
+};
+
+typedef struct avj_rowmap {
+  int32_t rows_per_group; /* 0 = identity */
+  int32_t group_stride;
+  int32_t row_offset;
+} avj_rowmap;
+
+/* Fused GEMM epilogue: C[map(r), n] (+)= act(acc + bias[n]) * gelu'(aux[r,n])
+ *                                        + residual[map(r), n] + pos[pos_idx[r], n]      */
+typedef struct avj_epilogue {
+  const float* bias;       /* [N] or NULL                                                  */
+  const float* residual;   /* fp32, same physical layout as C (ldc), or NULL               */
+  const float* pos;        /* fp32 [pos_rows, N] positional table, or NULL                 */
+  const int64_t* pos_idx;  /* [M] token ids into pos; NULL -> r % pos_rows                 */
+  int32_t pos_rows;
+  int32_t act;             /* 0 none, 1 exact-erf GELU                                     */
+  void* pre_out;           /* act!=0: also store the pre-activation, [M,N] ld=N, dtype     */
+  const void* dact_aux;    /* != NULL: multiply acc by gelu'(dact_aux[r,n]) ([M,N], dtype) */
+  int32_t accumulate;      /* 1: C += result (fp32 C only; weight gradients)               */
+  int32_t out_dtype;       /* AVJ_F32 or AVJ_BF16                                          */
+  avj_rowmap out_map;      /* physical row of C / residual for logical row r               */
+} avj_epilogue;
+
+int avj_version(void);
+const char* avj_last_error_string(void);
+/* 1 when the device behind the current context is sm_100 and the tcgen05 path is usable. */
+int avj_device_ok(void);
+
+/* ---- K6: nn.Linear fprop/dgrad/wgrad (src/models/utils/modules.py:25-36,54-77) and the
+ *      patch-embed / predictor-embed GEMMs (patch_embed.py:85-101, audiovisionpredictor.py:
+ *      232-243).  dtype selects the operand type of A and B. */
+int avj_gemm(int dtype, int layout, const void* A, const void* B, void* C,
+             int M, int N, int K, int lda, int ldb, int ldc,
+             const avj_epilogue* ep, void* stream);
+
+/* ---- K1/K2: tubelet / mel patch extraction feeding the patch-embed GEMM
+ *      (src/models/utils/patch_embed.py:98-102).  x is fp32 [B, C, T, H, W]; out row
+ *      r = b*K + j holds the flattened (c, dt, dh, dw) patch of token idx[r] (or token j
+ *      when idx == NULL, K == tokens per clip), i.e. the Conv3d weight's own K order, so
+ *      only the kept tokens are ever embedded.  Audio: C=1, T=1, tub=1. */
+int avj_patchify(const float* x, const int64_t* idx, void* out, int out_dtype,
+                 int B, int C, int T, int H, int W, int tub, int patch, int K, void* stream);
+
+/* ---- K3: apply_masks (src/masks/utils.py:14-34) for one mask, and its backward.
+ *      out[b, j, :] = x[b, idx[b, j], :];  bwd: dx[b, idx[b, j], :] += dout[b, j, :]. */
+int avj_gather_rows_fwd(int dtype, const void* x, const int64_t* idx, void* out,
+                        int B, int N, int K, int D, void* stream);
+int avj_gather_rows_bwd(int dtype, const void* dout, const int64_t* idx, void* dx,
+                        int B, int N, int K, int D, void* stream);
+
+/* ---- generic row-mapped copy / cast / accumulate:
+ *      out[omap(r), :] (=|+=) in[imap(r), :], r in [0, rows).  Replaces the torch.split /
+ *      torch.cat / .to(dtype) glue of app/avjepa/train.py:449-455,476-486 and
+ *      audiovisionpredictor.py:272-299. */
+int avj_copy_rows(const void* in, int in_dtype, int ld_in, avj_rowmap imap,
+                  void* out, int out_dtype, int ld_out, avj_rowmap omap,
+                  int rows, int D, int accumulate, void* stream);
+
+/* ---- K4: predictor target rows (audiovisionpredictor.py:245-269):
+ *      x[map(r), :] = mask_token[:] + pos[idx[r], :], r in [0, rows). */
+int avj_fill_mask_tokens(const float* mask_token, const float* pos, const int64_t* idx,
+                         float* x, int ld, avj_rowmap map, int rows, int D, void* stream);
+
+/* ---- column sum over mapped rows: out[n] += sum_r in[map(r), n]  (bias and mask-token
+ *      gradients).  ws: fp32 workspace of avj_colsum_ws_floats(rows, D) floats. */
+int64_t avj_colsum_ws_floats(int rows, int D);
+int avj_colsum(const void* in, int in_dtype, int ld, avj_rowmap map, float* out,
+               int rows, int D, float* ws, void* stream);
+
+/* ---- K5: nn.LayerNorm (modules.py:115,119; eps 1e-6) and F.layer_norm without affine
+ *      (app/avjepa/train.py:448; eps 1e-5).  x fp32 [rows, D]; y in y_dtype; gamma/beta may
+ *      be NULL (no affine); mean/rstd may be NULL (inference). */
+int avj_layernorm_fwd(const float* x, const float* gamma, const float* beta,
+                      void* y, int y_dtype, float* mean, float* rstd,
+                      int rows, int D, float eps, void* stream);
+/* dx_out = dres_in + LN'(dy) (fp32);  dx_lp: optional low-precision copy of dx_out (dtype
+ * lp_dtype) feeding the next dgrad/wgrad GEMM;  dgamma/dbeta are ACCUMULATED (may be NULL).
+ * ws: avj_layernorm_bwd_ws_floats(rows, D) floats. */
+int64_t avj_layernorm_bwd_ws_floats(int rows, int D);
+int avj_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma,
+                      const float* mean, const float* rstd, const float* dres_in,
+                      float* dx_out, void* dx_lp, int lp_dtype,
+                      float* dgamma, float* dbeta, float* ws,
+                      int rows, int D, void* stream);
+
+/* ---- K7: F.scaled_dot_product_attention(q, k, v) (modules.py:66-69): non-causal, no
+ *      mask, no dropout, scale = hd^-0.5.  qkv is the qkv-Linear output [B, N, 3, H, hd]
+ *      read in place (no permute copies); out is [B, N, H*hd]; lse fp32 [B, H, N]. */
+int avj_attention_fwd(int dtype, const void* qkv, void* out, float* lse,
+                      int B, int N, int H, int hd, float scale, void* stream);
+/* dqkv [B, N, 3, H, hd];  ws: avj_attention_bwd_ws_floats(B,N,H,hd) floats. */
+int64_t avj_attention_bwd_ws_floats(int B, int N, int H, int hd);
+int avj_attention_bwd(int dtype, const void* qkv, const void* out, const void* dout,
+                      const float* lse, void* dqkv, float* ws,
+                      int B, int N, int H, int hd, float scale, void* stream);
+
+/* ---- K10: latent loss sum_i mean(|z_i - h_i|^p)/p / n_masks (app/avjepa/train.py:490-495)
+ *      for ONE mask, forward + backward in one pass.  z, h fp32 [n].
+ *      loss_out[0] += (1/(n*n_masks*p)) * sum |z-h|^p ;  dz = grad_scale * d/dz of that term.
+ *      mode: 0 = |.|^p with p = loss_exp (reference), 1 = smooth-L1 with beta (extra).
+ *      ws: avj_loss_ws_floats(n) floats. */
+int64_t avj_loss_ws_floats(int64_t n);
+int avj_loss_fwd_bwd(const float* z, const float* h, float* dz, float* loss_out,
+                     int64_t n, int n_masks, float loss_exp, int mode, float beta,
+                     float grad_scale, float* ws, void* stream);
+/* token-variance regulariser value (app/avjepa/train.py:497-498,507-508): z fp32 [B,K,D] per
+ * mask; pstd[b,d] += sqrt(var_k(z)+1e-4)/n_masks.  Then avj_reg_finish reduces
+ * mean(relu(1-pstd)) into loss_reg[0]. */
+int avj_reg_accumulate(const float* z, float* pstd, int B, int K, int D, int n_masks, void* stream);
+int avj_reg_finish(const float* pstd, float* loss_reg, int n, void* stream);
+
+/* ---- K11-K13: AdamW (torch.optim.AdamW as built by app/avjepa/utils.py:228-282) fused with
+ *      grad unscale/clip, the EMA target update (app/avjepa/train.py:534-537), grad zeroing
+ *      and the bf16 shadow-weight refresh, over one contiguous parameter range.
+ *      scale_ptr: device float multiplied into every gradient (1/loss_scale * clip coef),
+ *      may be NULL.  target/p_lp/target_lp may be NULL. */
+typedef struct avj_adamw_args {
+  float* p; float* g; float* m; float* v;     /* fp32 [n]                                   */
+  float* target;                              /* EMA target fp32 [n] or NULL                */
+  void* p_lp; void* target_lp;                /* bf16 shadows or NULL                       */
+  int64_t n;
+  float lr, wd, beta1, beta2, eps;
+  int32_t step;                               /* 1-based                                    */
+  float ema_m;
+  int32_t skip_update;                        /* 1: frozen range -> EMA + shadows only      */
+  int32_t zero_grad;
+  const float* scale_ptr;
+} avj_adamw_args;
+int avj_adamw_ema_step(const avj_adamw_args* a, void* stream);
+
+/* sum of squares of a contiguous fp32 range -> out[0] (K13, clip_grad_norm_ train.py:518-520);
+ * ws: avj_sumsq_ws_floats(n).  avj_clip_coef: coef[0] = inv_loss_scale * min(1, max_norm /
+ * (sqrt(sumsq)*inv_loss_scale + 1e-6)), or just inv_loss_scale when max_norm <= 0. */
+int64_t avj_sumsq_ws_floats(int64_t n);
+int avj_sumsq(const float* x, int64_t n, float* out, float* ws, void* stream);
+int avj_clip_coef(const float* sumsq, float max_norm, float inv_loss_scale, float* coef, void* stream);
+
+/* fp32 -> bf16 (or fp32 copy) over a contiguous range: shadow-weight refresh. */
+int avj_cast(const float* in, void* out, int out_dtype, int64_t n, void* stream);
+/* stream-ordered zero fill of a raw device range (gradient / scatter targets). */
+int avj_memset_zero(void* ptr, int64_t nbytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVJEPA_B200_H_ */

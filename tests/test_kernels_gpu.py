@@ -1,0 +1,75 @@
+"""GPU kernel numerics: every C-ABI kernel against a plain PyTorch fp32 reference of the same op."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+F32, BF16 = 0, 1
+NT, NN, TN = 0, 1, 2
+
+GEMM_CASES = [
+    # (code, layout, M, N, K, epilogue)
+    (F32, NT, 100, 192, 192, 'bias'), (F32, NN, 77, 64, 136, 'none'), (F32, TN, 192, 64, 333, 'accum'),
+    (F32, NT, 130, 768, 192, 'bias_gelu'), (F32, NT, 64, 192, 768, 'bias_res'), (F32, NN, 96, 768, 192, 'dact'),
+    (F32, NT, 120, 192, 256, 'pos_map'),
+    (BF16, NT, 128, 256, 64, 'none'), (BF16, NT, 1000, 1024, 1024, 'bias'), (BF16, NT, 333, 576, 192, 'bias'),
+    (BF16, NT, 700, 768, 192, 'bias_gelu'), (BF16, NT, 515, 192, 768, 'bias_res'), (BF16, NT, 480, 384, 1536, 'pos_map'),
+    (BF16, NN, 128, 256, 64, 'none'), (BF16, NN, 900, 1024, 3072, 'none'), (BF16, NN, 650, 768, 192, 'dact'),
+    (BF16, TN, 128, 256, 64, 'accum'), (BF16, TN, 3072, 1024, 5000, 'accum'), (BF16, TN, 192, 1536, 777, 'accum'),
+    (BF16, TN, 384, 192, 130, 'accum'), (BF16, NT, 96, 1280, 1280, 'bias'), (BF16, NT, 50, 72, 64, 'bias'),
+]
+
+
+@pytest.mark.parametrize('code,layout,M,N,K,epi', GEMM_CASES)
+def test_gemm(code, layout, M, N, K, epi):
+    import kernel_checks as kc
+    ok, err = kc.check_gemm(code, layout, M, N, K, epi)
+    assert ok, f'rel err {err}'
+
+
+@pytest.mark.parametrize('code,rows,D,affine', [(F32, 333, 192, True), (BF16, 1000, 1024, True), (BF16, 77, 384, True),
+                                               (F32, 50, 1280, True), (F32, 64, 768, False)])
+def test_layernorm(code, rows, D, affine):
+    import kernel_checks as kc
+    ok, err = kc.check_layernorm(code, rows, D, affine)
+    assert ok, f'rel err {err}'
+
+
+@pytest.mark.parametrize('code,B,N,H,hd', [(F32, 2, 100, 3, 64), (F32, 1, 333, 2, 24), (BF16, 2, 257, 4, 64),
+                                          (BF16, 1, 130, 2, 24), (BF16, 1, 96, 2, 80), (BF16, 2, 40, 2, 128),
+                                          (F32, 1, 70, 2, 32)])
+def test_attention(code, B, N, H, hd):
+    import kernel_checks as kc
+    ok, err = kc.check_attention(code, B, N, H, hd)
+    assert ok, f'rel err {err}'
+
+
+@pytest.mark.parametrize('code', [F32, BF16])
+def test_gather_rows_bit_exact(code):
+    import kernel_checks as kc
+    ok, _ = kc.check_gather(code)
+    assert ok
+
+
+@pytest.mark.parametrize('code,audio', [(F32, False), (BF16, False), (F32, True), (BF16, True)])
+def test_patchify(code, audio):
+    import kernel_checks as kc
+    ok, err = kc.check_patchify(code, audio=audio)
+    assert ok, f'rel err {err}'
+
+
+def test_row_kernels():
+    import kernel_checks as kc
+    ok, err = kc.check_rows()
+    assert ok, err
+
+
+def test_loss():
+    import kernel_checks as kc
+    ok, err = kc.check_loss()
+    assert ok, err
+
+
+def test_adamw_ema():
+    import kernel_checks as kc
+    ok, err = kc.check_adamw()
+    assert ok, err

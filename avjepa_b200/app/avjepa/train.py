@@ -99,8 +99,11 @@ class TrainStep(object):
         loss.backward()
         if isinstance(opt, FusedAdamWEMA):
             opt.mark_grads_dirty()
+        # data parallel: ranks SUM their flat gradient buffers; the 1/world averaging is folded into
+        # the gradient multiplier the optimizer kernel applies anyway (no extra pass over the grads)
+        inv = 1.0
         if self.grad_sync is not None:
-            self.grad_sync.all_reduce(opt)
+            inv = self.grad_sync.all_reduce(opt, average=not isinstance(opt, FusedAdamWEMA))
         enc_norm = pred_norm = None
         coef = None
         if isinstance(opt, FusedAdamWEMA) and (epoch > self.warmup) and (self.clip_grad is not None):
@@ -108,13 +111,13 @@ class TrainStep(object):
             pred_sq = opt.grad_norm_sq(lambda r: r['group'] in (1, 3))
             ce, cp = torch.empty_like(enc_sq), torch.empty_like(pred_sq)
             from avjepa_b200 import _cabi, engine
-            _cabi.call('avj_clip_coef', enc_sq.data_ptr(), float(self.clip_grad), 1.0, ce.data_ptr(), engine.stream())
-            _cabi.call('avj_clip_coef', pred_sq.data_ptr(), float(self.clip_grad), 1.0, cp.data_ptr(), engine.stream())
+            _cabi.call('avj_clip_coef', enc_sq.data_ptr(), float(self.clip_grad), inv, ce.data_ptr(), engine.stream())
+            _cabi.call('avj_clip_coef', pred_sq.data_ptr(), float(self.clip_grad), inv, cp.data_ptr(), engine.stream())
             coef = {0: ce, 2: ce, 1: cp, 3: cp}
-            enc_norm, pred_norm = enc_sq.sqrt(), pred_sq.sqrt()
+            enc_norm, pred_norm = enc_sq.sqrt() * inv, pred_sq.sqrt() * inv
         m = next(self.momentum_scheduler)
         if isinstance(opt, FusedAdamWEMA):
-            opt.step(ema_momentum=m, coef_by_group=coef)
+            opt.step(ema_momentum=m, coef_by_group=coef, inv_loss_scale=inv)
             opt.zero_grad()
         else:       # stock optimizer: unfused EMA, reference order
             opt.step()

@@ -1,0 +1,417 @@
+// K7 flash-attention FORWARD on the 5th-gen tensor cores (sm_100a): S = Q K^T and O += P V are
+// tcgen05.mma instructions with their accumulators in TMEM; softmax runs on 128 threads that each own
+// one query row (= one TMEM lane).
+//
+//   warp 0      : loader -- cp.async 16-byte copies of Q / K / V head slices straight out of the
+//                 qkv-Linear output [B, N, 3, H, hd] into SWIZZLE_128B shared-memory tiles (zero
+//                 padding of hd -> HDP and of rows >= N happens here, in shared memory only)
+//   warp 1      : TMEM allocator + single-thread MMA issuer
+//   warps 2..5  : softmax: tcgen05.ld S (128 fp32 columns per row), running max / sum in fp32 with
+//                 exp2f, P -> bf16 -> swizzled smem (A operand of the PV MMA), lazy rescale of the
+//                 TMEM-resident O only when a row maximum moves by more than 2^8, final O / l
+//
+// CTA = 128 queries of one (batch, head); K/V tiles of 128 keys, double-buffered; S (128 cols) and
+// O (HDP cols) share a 256-column TMEM allocation so two CTAs fit per SM and overlap each other's
+// MMA and softmax phases.  S[t+1] is issued as soon as the softmax has pulled S[t] into registers.
+//
+// Roofline: MUFU-bound for hd <= 64 (one exp2 per score: 128x128 per tile per CTA) -- the tensor
+// pipe needs ~512 cycles per tile at hd = 64, the 16 exp2/clk/SM special-function units ~1024.
+// Algorithmic FLOPs: 4 * N^2 * hd per (batch, head).
+#include "common.cuh"
+
+#include <cuda.h>
+#include <mutex>
+#include <stdlib.h>
+#include <utility>
+#include <vector>
+
+#define UA_BM 128
+#define UA_BN 128
+#define UA_THREADS 192
+#define UA_TILE_BYTES (128 * 128)                 // 128 rows x 128 B (one swizzle atom wide)
+#define UA_SMEM_BYTES (UA_TILE_BYTES * (1 + 2 + 2 + 2) + 256)   // Q, K[2], V[2], P(2 atoms) + barriers
+#define UA_TMEM_COLS 256
+#define UA_O_COL 128
+
+__device__ __forceinline__ uint32_t ua_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ua_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void ua_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void ua_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void ua_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void ua_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void ua_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void ua_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void ua_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ uint64_t ua_desc(uint32_t saddr, uint32_t lbo16, uint32_t sbo16) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(lbo16 & 0x3FFF) << 16) | ((uint64_t)(sbo16 & 0x3FFF) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void ua_cp16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+}
+__device__ __forceinline__ void ua_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void ua_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void ua_st32(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+        "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+        "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+        "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+        "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// One warp stages 128 rows x HDP bf16 (hd real columns, rest zero) into a SWIZZLE_128B tile:
+// 16-byte chunk c of row r lands at r*128 + ((c ^ (r & 7)) << 4).
+template <int HDP>
+__device__ __forceinline__ void ua_stage(uint32_t tile, const bf16* __restrict__ src, int64_t row_stride, int row0,
+                                         int nrows_total, int hd, int lane) {
+  constexpr int CH = HDP / 8;
+  const int hd_ch = hd / 8;
+  for (int e = lane; e < 128 * CH; e += 32) {
+    const int r = e / CH, c = e % CH;
+    const uint32_t dst = tile + r * 128 + ((c ^ (r & 7)) << 4);
+    if (row0 + r < nrows_total && c < hd_ch) {
+      ua_cp16(dst, src + (int64_t)(row0 + r) * row_stride + c * 8);
+    } else {
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+    }
+  }
+}
+
+// 3-D TMA load of one 128-row x 64-col bf16 box of the qkv tensor viewed as {3*H*hd, N, B}
+__device__ __forceinline__ void ua_tma3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void ua_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+// TMA = true (hd == 64): one elected thread issues 16 KB box loads (rows past N are zero-filled by
+// the hardware); TMA = false: the loader warp gathers 16-byte chunks with cp.async and pads in smem.
+template <int HDP, bool TMA>
+__global__ void __launch_bounds__(UA_THREADS, 2)
+fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restrict__ qkv, bf16* __restrict__ out,
+                   float* __restrict__ lse, int N, int H, int hd, float scale_log2) {
+  extern __shared__ __align__(1024) uint8_t ua_raw[];
+  const uint32_t base = ua_smem(ua_raw);
+  const uint32_t sQ = base;
+  const uint32_t sK = sQ + UA_TILE_BYTES;            // [2]
+  const uint32_t sV = sK + 2 * UA_TILE_BYTES;        // [2]
+  const uint32_t sP = sV + 2 * UA_TILE_BYTES;        // 2 atoms of 64 keys
+  const uint32_t bars = sP + 2 * UA_TILE_BYTES;
+  const uint32_t kv_full = bars;            // [2] count 32
+  const uint32_t kv_empty = bars + 16;      // [2] count 1
+  const uint32_t s_full = bars + 32;        // count 1
+  const uint32_t s_free = bars + 40;        // count 128
+  const uint32_t p_full = bars + 48;        // count 128
+  const uint32_t o_done = bars + 56;        // count 1
+  const uint32_t tmem_slot = bars + 64;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(ua_raw + (tmem_slot - base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * UA_BM;
+  const int64_t rs = 3 * (int64_t)H * hd;
+  const bf16* qb = qkv + (int64_t)b * N * rs + (int64_t)h * hd;
+  const bf16* kb = qb + (int64_t)H * hd;
+  const bf16* vb = kb + (int64_t)H * hd;
+  const int T = (N + UA_BN - 1) / UA_BN;
+
+  if (threadIdx.x == 0) {
+    if (base & 1023u) __trap();                      // SWIZZLE_128B tiles need 1024-byte alignment
+    ua_mbar_init(kv_full, TMA ? 1 : 32); ua_mbar_init(kv_full + 8, TMA ? 1 : 32);
+    ua_mbar_init(kv_empty, 1); ua_mbar_init(kv_empty + 8, 1);
+    ua_mbar_init(s_full, 1); ua_mbar_init(s_free, 128); ua_mbar_init(p_full, 128); ua_mbar_init(o_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)UA_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  ua_fence_before();
+  __syncthreads();
+  ua_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ============================ loader ============================
+    if (TMA) {
+      if (lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+        const int cq = h * hd, ck = (H + h) * hd, cv = (2 * H + h) * hd;
+        for (int t = 0; t < T; ++t) {
+          const int st = t & 1;
+          if (t >= 2) ua_mbar_wait(kv_empty + 8 * st, ((t >> 1) & 1) ^ 1);
+          const uint32_t fb = kv_full + 8 * st;
+          ua_expect_tx(fb, (t == 0 ? 3 : 2) * UA_TILE_BYTES);
+          if (t == 0) ua_tma3d(sQ, &tmap, fb, cq, q0, b);
+          ua_tma3d(sK + st * UA_TILE_BYTES, &tmap, fb, ck, t * UA_BN, b);
+          ua_tma3d(sV + st * UA_TILE_BYTES, &tmap, fb, cv, t * UA_BN, b);
+        }
+      }
+    } else {
+      // software-pipelined gather: tile t+1 is in flight while tile t is being waited for
+      ua_stage<HDP>(sQ, qb, rs, q0, N, hd, lane);
+      ua_stage<HDP>(sK, kb, rs, 0, N, hd, lane);
+      ua_stage<HDP>(sV, vb, rs, 0, N, hd, lane);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      for (int t = 0; t < T; ++t) {
+        if (t + 1 < T) {
+          const int s1 = (t + 1) & 1;
+          if (t + 1 >= 2) ua_mbar_wait(kv_empty + 8 * s1, (((t + 1) >> 1) & 1) ^ 1);
+          ua_stage<HDP>(sK + s1 * UA_TILE_BYTES, kb, rs, (t + 1) * UA_BN, N, hd, lane);
+          ua_stage<HDP>(sV + s1 * UA_TILE_BYTES, vb, rs, (t + 1) * UA_BN, N, hd, lane);
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        ua_fence_async_smem();
+        ua_mbar_arrive(kv_full + 8 * (t & 1));
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UA_BN >> 3) << 17) | ((uint32_t)(UA_BM >> 4) << 24);
+      const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HDP >> 3) << 17) | ((uint32_t)(UA_BM >> 4) << 24);
+      const uint64_t qd = ua_desc(sQ, 1, 64);
+      auto issue_s = [&](int t) {
+        const uint64_t kd = ua_desc(sK + (t & 1) * UA_TILE_BYTES, 1, 64);
+#pragma unroll
+        for (int k = 0; k < HDP / 16; ++k) ua_mma(tmem, qd + 2 * k, kd + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        ua_commit(s_full);
+      };
+      ua_mbar_wait(kv_full, 0);
+      ua_fence_after();
+      issue_s(0);
+      for (int t = 0; t < T; ++t) {
+        if (t + 1 < T) {
+          ua_mbar_wait(kv_full + 8 * ((t + 1) & 1), ((t + 1) >> 1) & 1);
+          ua_mbar_wait(s_free, t & 1);                 // softmax has S[t] in registers
+          ua_fence_after();
+          issue_s(t + 1);
+        }
+        ua_mbar_wait(p_full, t & 1);
+        ua_fence_after();
+        const uint32_t vt = sV + (t & 1) * UA_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < UA_BN / 16; ++k) {
+          const uint64_t pd = ua_desc(sP + (k >> 2) * UA_TILE_BYTES, 1, 64) + 2 * (k & 3);
+          const uint64_t vd = ua_desc(vt, 512, 64) + 128 * k;        // MN-major: 16 keys = 2048 B per step
+          ua_mma(tmem + UA_O_COL, pd, vd, idesc_o, (t > 0 || k > 0) ? 1u : 0u);
+        }
+        ua_commit(o_done);
+        ua_commit(kv_empty + 8 * (t & 1));
+      }
+    }
+  } else {
+    // ============================ softmax ============================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                                   // TMEM lane == query row in tile
+    const uint32_t t_s = tmem + ((uint32_t)(q * 32) << 16);
+    const uint32_t t_o = t_s + UA_O_COL;
+    float m = -INFINITY, l = 0.f;
+    for (int t = 0; t < T; ++t) {
+      ua_mbar_wait(s_full, t & 1);
+      ua_fence_after();
+      float s[128];
+      ua_ld32(t_s, s); ua_ld32(t_s + 32, s + 32); ua_ld32(t_s + 64, s + 64); ua_ld32(t_s + 96, s + 96);
+      ua_ld_wait();
+      ua_fence_before();
+      ua_mbar_arrive(s_free);
+      const int nvalid = N - t * UA_BN;
+      if (nvalid < UA_BN) {
+#pragma unroll
+        for (int j = 0; j < 128; ++j) if (j >= nvalid) s[j] = -INFINITY;
+      }
+      float tmax = s[0];
+#pragma unroll
+      for (int j = 1; j < 128; ++j) tmax = fmaxf(tmax, s[j]);
+      const float m_new = fmaxf(m, tmax);
+      // lazy rescale: keep the stale maximum unless it is off by more than 2^8
+      const bool jump = (m_new - m) * scale_log2 > 8.0f;             // true for t == 0 (m = -inf)
+      const float m_use = jump ? m_new : m;
+      const float corr = exp2f((m - m_use) * scale_log2);            // 1 when unchanged, 0 at t == 0
+      const float mb = m_use * scale_log2;
+      float rsum = 0.f;
+      uint32_t pk[64];
+#pragma unroll
+      for (int j = 0; j < 128; j += 2) {
+        const float p0 = exp2f(fmaf(s[j], scale_log2, -mb));
+        const float p1 = exp2f(fmaf(s[j + 1], scale_log2, -mb));
+        rsum += p0 + p1;
+        pk[j >> 1] = pack_bf16x2(p0, p1);
+      }
+      l = l * corr + rsum;
+      m = m_use;
+      if (t > 0) ua_mbar_wait(o_done, (t - 1) & 1);                  // PV[t-1] finished: P smem and O are ours
+      ua_fence_after();
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {                                 // 16 chunks of 8 keys
+        const uint32_t dst = sP + (c >> 3) * UA_TILE_BYTES + row * 128 + (((c & 7) ^ (row & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
+                     "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
+      }
+      if (t > 0 && __any_sync(0xffffffffu, jump)) {
+        float o[32];
+#pragma unroll
+        for (int c = 0; c < HDP; c += 32) {
+          ua_ld32(t_o + c, o);
+          ua_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] *= corr;
+          ua_st32(t_o + c, o);
+        }
+      }
+      ua_fence_async_smem();
+      ua_fence_before();
+      ua_mbar_arrive(p_full);
+    }
+    ua_mbar_wait(o_done, (T - 1) & 1);
+    ua_fence_after();
+    const int qi = q0 + row;
+    const float inv = 1.f / l;
+    bf16* orow = out + ((int64_t)b * N + qi) * (int64_t)H * hd + (int64_t)h * hd;
+#pragma unroll
+    for (int c = 0; c < HDP; c += 32) {
+      float o[32];
+      ua_ld32(t_o + c, o);
+      ua_ld_wait();
+      if (qi < N) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          if (c + j < hd) {
+            float v8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v8[e] = o[j + e] * inv;
+            store8<bf16>(orow + c + j, v8);
+          }
+        }
+      }
+    }
+    if (qi < N) lse[((int64_t)b * H + h) * N + qi] = (m * scale_log2 + log2f(l)) * 0.69314718055994530942f;
+  }
+
+  ua_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ua_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)UA_TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------
+bool avj_attention_umma_fwd_supported(int dtype, int hd) {
+  return dtype == AVJ_BF16 && hd % 8 == 0 && hd >= 8 && hd <= 64;
+}
+
+typedef CUresult (*PFN_ua_encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// qkv [B, N, 3*H*hd] bf16 viewed as a 3-D tensor {cols, N, B}; box = {64 cols, 128 rows, 1}, SWIZZLE_128B.
+static int ua_qkv_map(const void* qkv, int B, int N, int cols, CUtensorMap* out) {
+  struct Key { const void* p; int B, N, cols; };
+  static std::mutex mu;
+  static std::vector<std::pair<Key, CUtensorMap>> cache;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    for (auto& e : cache)
+      if (e.first.p == qkv && e.first.B == B && e.first.N == N && e.first.cols == cols) { *out = e.second; return 0; }
+  }
+  static PFN_ua_encode enc = nullptr;
+  if (!enc) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      enc = reinterpret_cast<PFN_ua_encode>(p);
+  }
+  AVJ_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)N, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)cols * 2 * (cuuint64_t)N};
+  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AVJ_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(qkv) failed (%d)", (int)r);
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 512) cache.clear();
+  cache.push_back({Key{qkv, B, N, cols}, *out});
+  return 0;
+}
+
+template <int HDP, bool TMA>
+static int ua_launch(const bf16* qkv, bf16* out, float* lse, int B, int N, int H, int hd, float scale, cudaStream_t s) {
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(fa_fwd_umma_kernel<HDP, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, UA_SMEM_BYTES);
+    AVJ_CHECK(e == cudaSuccess, "cudaFuncSetAttribute(fa_fwd_umma_kernel) failed: %s", cudaGetErrorString(e));
+    // two CTAs per SM need the full 228 KB shared-memory carve-out
+    cudaFuncSetAttribute(fa_fwd_umma_kernel<HDP, TMA>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    set = true;
+  }
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  if (TMA) {
+    int rc = ua_qkv_map(qkv, B, N, 3 * H * hd, &map);
+    if (rc) return rc;
+  }
+  dim3 grid((N + UA_BM - 1) / UA_BM, H, B);
+  fa_fwd_umma_kernel<HDP, TMA><<<grid, UA_THREADS, UA_SMEM_BYTES, s>>>(map, qkv, out, lse, N, H, hd, scale * 1.4426950408889634f);
+  AVJ_LAUNCH_CHECK();
+  return 0;
+}
+
+int avj_attention_fwd_umma(const void* qkv, void* out, float* lse, int B, int N, int H, int hd, float scale, cudaStream_t s) {
+  static int use_tma = -1;
+  if (use_tma < 0) { const char* e = getenv("AVJ_ATTN_TMA"); use_tma = (e && e[0] == '0') ? 0 : 1; }
+  if (hd <= 32) return ua_launch<32, false>((const bf16*)qkv, (bf16*)out, lse, B, N, H, hd, scale, s);
+  if (hd == 64 && use_tma && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0)
+    return ua_launch<64, true>((const bf16*)qkv, (bf16*)out, lse, B, N, H, hd, scale, s);
+  return ua_launch<64, false>((const bf16*)qkv, (bf16*)out, lse, B, N, H, hd, scale, s);
+}

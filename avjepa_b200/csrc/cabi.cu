@@ -19,6 +19,16 @@ int avj_attention_fwd_mma(const void* qkv, void* out, float* lse, int B, int N, 
 int avj_attention_bwd_mma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                           float* ws, int B, int N, int H, int hd, float scale, cudaStream_t s);
 
+bool avj_attention_umma_fwd_supported(int dtype, int hd);
+int avj_attention_fwd_umma(const void* qkv, void* out, float* lse, int B, int N, int H, int hd, float scale, cudaStream_t s);
+
+// AVJ_ATTN_FWD = umma (default) | mma : which tensor-core forward kernel serves bf16 attention
+static bool attn_fwd_use_umma() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("AVJ_ATTN_FWD"); v = (e && e[0] == 'm') ? 0 : 1; }
+  return v == 1;
+}
+
 static bool force_simt() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("AVJ_FORCE_SIMT"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -57,6 +67,8 @@ extern "C" int avj_attention_fwd(int dtype, const void* qkv, void* out, float* l
                                  int B, int N, int H, int hd, float scale, void* stream) {
   AVJ_CHECK(hd > 0 && hd <= 128, "avj_attention_fwd: head_dim %d out of range (1..128)", hd);
   if (B == 0 || N == 0) return 0;
+  if (!force_simt_attn() && attn_fwd_use_umma() && avj_attention_umma_fwd_supported(dtype, hd))
+    return avj_attention_fwd_umma(qkv, out, lse, B, N, H, hd, scale, as_stream(stream));
   if (!force_simt_attn() && avj_attention_mma_supported(dtype, hd))
     return avj_attention_fwd_mma(qkv, out, lse, B, N, H, hd, scale, as_stream(stream));
   return avj_attention_fwd_simt(dtype, qkv, out, lse, B, N, H, hd, scale, as_stream(stream));

@@ -104,6 +104,30 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
+// Abramowitz-Stegun 7.1.26 erf (|abs err| <= 1.5e-7): one MUFU.EX2 + one MUFU.RCP + 7 FMA.  Used when the
+// result is rounded to bf16 anyway (production mode); fp32 check mode keeps erff().
+__device__ __forceinline__ void gelu_fast_parts(float x, float& cdf, float& pdf) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float e = __expf(-z * z);                       // = exp(-x^2/2)
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float erf_abs = 1.0f - p * t * e;               // erf(|x|/sqrt2)
+  const float erf_v = copysignf(erf_abs, x);
+  cdf = 0.5f * (1.0f + erf_v);
+  pdf = 0.39894228040143267794f * e;
+}
+template <bool FAST> __device__ __forceinline__ float gelu_fwd(float x) {
+  if (FAST) { float c, p; gelu_fast_parts(x, c, p); return x * c; }
+  return gelu_erf(x);
+}
+template <bool FAST> __device__ __forceinline__ float gelu_bwd(float x) {
+  if (FAST) { float c, p; gelu_fast_parts(x, c, p); return c + x * p; }
+  return gelu_erf_grad(x);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -130,11 +154,47 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 }
 
 // ---- shared GEMM epilogue (used by the SIMT check-mode GEMM and the tcgen05 GEMM) ----------
-// Applies the avj_epilogue to `NV` consecutive accumulator columns of logical row r starting at
-// column n0 (all in range: caller clips), and stores them.  NV must be a multiple of 4.
-template <typename TAct, int NV>
+// epilogue_prefetch gathers everything that is ADDED to the activated accumulator (fp32 residual row,
+// gathered positional row, previous C for `C +=`) into registers; it does not depend on the
+// accumulator, so the tcgen05 kernel issues it while the TMEM load is still in flight.
+template <int NV>
+__device__ __forceinline__ void epilogue_prefetch(const avj_epilogue& ep, const void* C, int ldc, int N,
+                                                  int64_t r, int n0, float (&add)[NV]) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) add[i] = 0.f;
+  const int64_t pr = map_row(ep.out_map, r);
+  if (ep.residual) {
+    const float* res = ep.residual + pr * (int64_t)ldc + n0;
+#pragma unroll
+    for (int i = 0; i < NV; i += 4) {
+      float4 b = *reinterpret_cast<const float4*>(res + i);
+      add[i] += b.x; add[i + 1] += b.y; add[i + 2] += b.z; add[i + 3] += b.w;
+    }
+  }
+  if (ep.pos) {
+    const int64_t prow = ep.pos_idx ? ep.pos_idx[r] : (r % ep.pos_rows);
+    const float* pp = ep.pos + prow * (int64_t)N + n0;
+#pragma unroll
+    for (int i = 0; i < NV; i += 4) {
+      float4 b = *reinterpret_cast<const float4*>(pp + i);
+      add[i] += b.x; add[i + 1] += b.y; add[i + 2] += b.z; add[i + 3] += b.w;
+    }
+  }
+  if (ep.accumulate && ep.out_dtype == AVJ_F32) {
+    const float* out = reinterpret_cast<const float*>(C) + pr * (int64_t)ldc + n0;
+#pragma unroll
+    for (int i = 0; i < NV; i += 4) {
+      float4 b = *reinterpret_cast<const float4*>(out + i);
+      add[i] += b.x; add[i + 1] += b.y; add[i + 2] += b.z; add[i + 3] += b.w;
+    }
+  }
+}
+
+// Applies bias / activation / GELU' to NV consecutive accumulator columns of logical row r starting
+// at column n0, adds the prefetched addend and stores.  NV must be a multiple of 8.
+template <typename TAct, int NV, bool FAST>
 __device__ __forceinline__ void epilogue_apply_store(const avj_epilogue& ep, void* C, int ldc, int N,
-                                                     int64_t r, int n0, float (&acc)[NV]) {
+                                                     int64_t r, int n0, float (&acc)[NV], const float (&add)[NV]) {
   if (ep.bias) {
 #pragma unroll
     for (int i = 0; i < NV; i += 4) {
@@ -154,7 +214,7 @@ __device__ __forceinline__ void epilogue_apply_store(const avj_epilogue& ep, voi
       }
     }
 #pragma unroll
-    for (int i = 0; i < NV; ++i) acc[i] = gelu_erf(acc[i]);
+    for (int i = 0; i < NV; ++i) acc[i] = gelu_fwd<FAST>(acc[i]);
   }
   if (ep.dact_aux) {
     const TAct* aux = reinterpret_cast<const TAct*>(ep.dact_aux) + r * (int64_t)N + n0;
@@ -163,36 +223,14 @@ __device__ __forceinline__ void epilogue_apply_store(const avj_epilogue& ep, voi
       float t[8];
       load8<TAct>(aux + i, t);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i + j] *= gelu_erf_grad(t[j]);
+      for (int j = 0; j < 8; ++j) acc[i + j] *= gelu_bwd<FAST>(t[j]);
     }
   }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] += add[i];
   const int64_t pr = map_row(ep.out_map, r);
-  if (ep.residual) {
-    const float* res = ep.residual + pr * (int64_t)ldc + n0;
-#pragma unroll
-    for (int i = 0; i < NV; i += 4) {
-      float4 b = *reinterpret_cast<const float4*>(res + i);
-      acc[i] += b.x; acc[i + 1] += b.y; acc[i + 2] += b.z; acc[i + 3] += b.w;
-    }
-  }
-  if (ep.pos) {
-    const int64_t prow = ep.pos_idx ? ep.pos_idx[r] : (r % ep.pos_rows);
-    const float* pp = ep.pos + prow * (int64_t)N + n0;
-#pragma unroll
-    for (int i = 0; i < NV; i += 4) {
-      float4 b = *reinterpret_cast<const float4*>(pp + i);
-      acc[i] += b.x; acc[i + 1] += b.y; acc[i + 2] += b.z; acc[i + 3] += b.w;
-    }
-  }
   if (ep.out_dtype == AVJ_F32) {
     float* out = reinterpret_cast<float*>(C) + pr * (int64_t)ldc + n0;
-    if (ep.accumulate) {
-#pragma unroll
-      for (int i = 0; i < NV; i += 4) {
-        float4 b = *reinterpret_cast<const float4*>(out + i);
-        acc[i] += b.x; acc[i + 1] += b.y; acc[i + 2] += b.z; acc[i + 3] += b.w;
-      }
-    }
 #pragma unroll
     for (int i = 0; i < NV; i += 4)
       *reinterpret_cast<float4*>(out + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);

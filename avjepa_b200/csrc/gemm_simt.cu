@@ -68,7 +68,11 @@ gemm_simt_kernel(const T* __restrict__ A, const T* __restrict__ B, void* __restr
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = m0 + ty * 4 + i;
-    if (r < M) epilogue_apply_store<T, 8>(ep, C, ldc, N, r, nc, acc[i]);
+    if (r < M) {
+      float add[8];
+      epilogue_prefetch<8>(ep, C, ldc, N, r, nc, add);
+      epilogue_apply_store<T, 8, false>(ep, C, ldc, N, r, nc, acc[i], add);
+    }
   }
 }
 

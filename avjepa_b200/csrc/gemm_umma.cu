@@ -27,7 +27,8 @@
 #define UG_STAGES 4
 #define UG_A_STAGE_BYTES (UG_BM * UG_BK * 2)        // 16 KB
 #define UG_B_STAGE_BYTES (UG_MAX_BN * UG_BK * 2)    // 32 KB
-#define UG_THREADS 192
+#define UG_EPI_WARPS 8
+#define UG_THREADS (64 + 32 * UG_EPI_WARPS)
 #define UG_SMEM_BYTES (UG_STAGES * (UG_A_STAGE_BYTES + UG_B_STAGE_BYTES) + 1024 + 256)
 
 struct UmmaParams {
@@ -92,8 +93,7 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -104,10 +104,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor, SWIZZLE_128B, sm_100 version field = 1
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo16, uint32_t sbo16) {
@@ -140,7 +138,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
     for (int i = 0; i < UG_STAGES; ++i) { mbar_init(full_bar + 8 * i, 1); mbar_init(empty_bar + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + 8 * i, 1); mbar_init(tempty_bar + 8 * i, 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + 8 * i, 1); mbar_init(tempty_bar + 8 * i, 32 * UG_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -223,7 +221,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else {
     // ================= epilogue warps =================
+    // 8 warps: two per TMEM lane quarter, each taking half of the tile's columns.
     const int q = warp & 3;                          // TMEM lane quarter this warp may touch
+    const int half = (warp - 2) >> 2;
+    const int c_lo = half * (p.block_n / 2), c_hi = c_lo + p.block_n / 2;
     uint32_t acc = 0, acc_phase = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
       const int tile = u / p.split_k;
@@ -232,17 +233,24 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       tc_fence_after();
       const int64_t row = (int64_t)m_blk * UG_BM + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * UG_MAX_BN;
-      for (int c = 0; c < p.block_n; c += 32) {
-        float v[32];
-        tmem_ld32(taddr + c, v);
+      const bool row_ok = row < p.M;
+      for (int c = c_lo; c < c_hi; c += 32) {
+        uint32_t raw[32];
+        tmem_ld32_issue(taddr + c, raw);
         const int n0 = n_blk * p.block_n + c;
-        if (row < p.M && n0 < p.N) {
+        float add[32];
+        if (p.split_k == 1 && row_ok) epilogue_prefetch<32>(p.ep, p.C, p.ldc, p.N, row, n0, add);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+        if (row_ok) {
           if (p.split_k > 1) {
             float* out = reinterpret_cast<float*>(p.C) + map_row(p.ep.out_map, row) * (int64_t)p.ldc + n0;
 #pragma unroll
             for (int i = 0; i < 32; i += 4) atomicAdd(reinterpret_cast<float4*>(out + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
           } else {
-            epilogue_apply_store<TAct, 32>(p.ep, p.C, p.ldc, p.N, row, n0, v);
+            epilogue_apply_store<TAct, 32, true>(p.ep, p.C, p.ldc, p.N, row, n0, v, add);
           }
         }
       }

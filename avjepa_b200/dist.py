@@ -44,9 +44,12 @@ class GradSync(object):
         self.bucket_elems = bucket_bytes // 4
         self.group = group
 
-    def all_reduce_flat(self, flats):
+    def all_reduce_flat(self, flats, average=True):
+        """SUM every flat buffer across ranks in bucket-sized chunks.  With average=False the
+        caller applies the returned 1/world factor itself (the fused optimizer folds it into its
+        gradient multiplier).  Returns the factor still owed (1.0 when already applied)."""
         if self.world_size <= 1:
-            return
+            return 1.0
         works = []
         for g in flats:
             n = g.numel()
@@ -56,8 +59,15 @@ class GradSync(object):
         for w in works:
             w.wait()
         inv = 1.0 / self.world_size
+        if not average:
+            return inv
         for g in flats:
             g.mul_(inv)
+        return 1.0
 
-    def all_reduce(self, optimizer):
-        self.all_reduce_flat(optimizer.flat_grads())
+    def all_reduce(self, optimizer, average=True):
+        if hasattr(optimizer, 'flat_grads'):
+            flats = optimizer.flat_grads()
+        else:
+            flats = [p.grad for grp in optimizer.param_groups for p in grp['params'] if p.grad is not None]
+        return self.all_reduce_flat(flats, average=average)

@@ -42,6 +42,34 @@ class AdamWArgs(C.Structure):
     ]
 
 
+class LinearWS(C.Structure):
+    _fields_ = [('w', C.c_void_p), ('b', C.c_void_p), ('gw', C.c_void_p), ('gb', C.c_void_p)]
+
+
+class NormWS(C.Structure):
+    _fields_ = [('w', C.c_void_p), ('b', C.c_void_p), ('gw', C.c_void_p), ('gb', C.c_void_p),
+                ('eps', C.c_float), ('pad_', C.c_int32)]
+
+
+class Layer(C.Structure):
+    _fields_ = [
+        ('n1', NormWS), ('qkv', LinearWS), ('proj', LinearWS), ('n2', NormWS), ('fc1', LinearWS), ('fc2', LinearWS),
+        ('x', C.c_void_p), ('mean1', C.c_void_p), ('rstd1', C.c_void_p), ('h1', C.c_void_p), ('qkv_act', C.c_void_p),
+        ('o', C.c_void_p), ('lse', C.c_void_p), ('x1', C.c_void_p), ('mean2', C.c_void_p), ('rstd2', C.c_void_p),
+        ('h2', C.c_void_p), ('pre', C.c_void_p), ('act', C.c_void_p), ('x_out', C.c_void_p),
+    ]
+
+
+class Stack(C.Structure):
+    _fields_ = [('dtype', C.c_int32), ('B', C.c_int32), ('N', C.c_int32), ('D', C.c_int32), ('H', C.c_int32),
+                ('hidden', C.c_int32), ('L', C.c_int32)]
+
+
+class StackScratch(C.Structure):
+    _fields_ = [('dxa', C.c_void_p), ('dxb', C.c_void_p), ('dx_lp', C.c_void_p), ('d_hid', C.c_void_p),
+                ('d_qkv', C.c_void_p), ('d_h', C.c_void_p), ('d_o', C.c_void_p), ('ws', C.c_void_p)]
+
+
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 # name -> (restype, argtypes); mirrors include/avjepa_b200.h one to one
@@ -73,6 +101,8 @@ PROTOTYPES = {
     'avj_clip_coef': (_i, [_vp, _f, _f, _vp, _vp]),
     'avj_cast': (_i, [_vp, _vp, _i, _i64, _vp]),
     'avj_memset_zero': (_i, [_vp, _i64, _vp]),
+    'avj_stack_forward': (_i, [C.POINTER(Stack), C.POINTER(Layer), _vp]),
+    'avj_stack_backward': (_i, [C.POINTER(Stack), C.POINTER(Layer), C.POINTER(StackScratch), _vp]),
 }
 
 _lib = None
@@ -113,8 +143,9 @@ def check(rc, what):
 launch_count = 0
 
 
-def call(name, *args):
+def call(name, *args, launches=1):
+    """`launches`: how many kernels the entry point issues (whole-stack schedules issue many)."""
     global launch_count
     lib = load()
-    launch_count += 1
+    launch_count += launches
     check(getattr(lib, name)(*args), name)

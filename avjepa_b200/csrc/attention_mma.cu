@@ -463,6 +463,17 @@ static int fwd_launch(const bf16* qkv, bf16* out, float* lse, int B, int N, int 
   return 0;
 }
 
+// delta[b,h,i] = sum_d dO . O into `delta` ([B, H, N] fp32); shared with the tcgen05 backward.
+int avj_attention_delta(const void* out, const void* dout, float* delta, int B, int N, int H, int hd, cudaStream_t s) {
+  const int64_t warps = (int64_t)B * N * H;
+  int grid = (int)((warps + 7) / 8);
+  const int cap = avj_num_sms() * 16;
+  if (grid > cap) grid = cap;
+  fa_delta_kernel<<<grid, 256, 0, s>>>((const bf16*)out, (const bf16*)dout, delta, B, N, H, hd);
+  AVJ_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int HP>
 static int bwd_launch(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, float* ws,
                       int B, int N, int H, int hd, float scale, cudaStream_t s) {

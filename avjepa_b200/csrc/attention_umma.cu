@@ -19,7 +19,7 @@
 // Algorithmic FLOPs: 4 * N^2 * hd per (batch, head).
 #include "common.cuh"
 
-#include <cuda.h>
+#include "umma_attn.cuh"
 #include <mutex>
 #include <stdlib.h>
 #include <utility>
@@ -32,100 +32,6 @@
 #define UA_SMEM_BYTES (UA_TILE_BYTES * (1 + 2 + 2 + 2) + 256)   // Q, K[2], V[2], P(2 atoms) + barriers
 #define UA_TMEM_COLS 256
 #define UA_O_COL 128
-
-__device__ __forceinline__ uint32_t ua_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ua_mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void ua_mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void ua_mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void ua_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void ua_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void ua_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void ua_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void ua_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ uint64_t ua_desc(uint32_t saddr, uint32_t lbo16, uint32_t sbo16) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(lbo16 & 0x3FFF) << 16) | ((uint64_t)(sbo16 & 0x3FFF) << 32) |
-         (1ull << 46) | (2ull << 61);
-}
-__device__ __forceinline__ void ua_cp16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
-}
-__device__ __forceinline__ void ua_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void ua_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void ua_st32(uint32_t taddr, const float* v) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      ::"r"(taddr),
-        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
-        "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
-        "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
-        "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
-        "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
-      : "memory");
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-
-// One warp stages 128 rows x HDP bf16 (hd real columns, rest zero) into a SWIZZLE_128B tile:
-// 16-byte chunk c of row r lands at r*128 + ((c ^ (r & 7)) << 4).
-template <int HDP>
-__device__ __forceinline__ void ua_stage(uint32_t tile, const bf16* __restrict__ src, int64_t row_stride, int row0,
-                                         int nrows_total, int hd, int lane) {
-  constexpr int CH = HDP / 8;
-  const int hd_ch = hd / 8;
-  for (int e = lane; e < 128 * CH; e += 32) {
-    const int r = e / CH, c = e % CH;
-    const uint32_t dst = tile + r * 128 + ((c ^ (r & 7)) << 4);
-    if (row0 + r < nrows_total && c < hd_ch) {
-      ua_cp16(dst, src + (int64_t)(row0 + r) * row_stride + c * 8);
-    } else {
-      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
-    }
-  }
-}
-
-// 3-D TMA load of one 128-row x 64-col bf16 box of the qkv tensor viewed as {3*H*hd, N, B}
-__device__ __forceinline__ void ua_tma3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void ua_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
 
 // TMA = true (hd == 64): one elected thread issues 16 KB box loads (rows past N are zero-filled by
 // the hardware); TMA = false: the loader warp gathers 16-byte chunks with cp.async and pads in smem.
@@ -190,24 +96,23 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
         }
       }
     } else {
-      // software-pipelined gather: tile t+1 is in flight while tile t is being waited for
+      // gather tile t+1 while the tensor core works on tile t.  kv_full[t] must be signalled BEFORE
+      // waiting for the stage of tile t+1 to drain (the MMA warp issues S(t+1) ahead of PV(t)).
       ua_stage<HDP>(sQ, qb, rs, q0, N, hd, lane);
       ua_stage<HDP>(sK, kb, rs, 0, N, hd, lane);
       ua_stage<HDP>(sV, vb, rs, 0, N, hd, lane);
       asm volatile("cp.async.commit_group;" ::: "memory");
       for (int t = 0; t < T; ++t) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        ua_fence_async_smem();
+        ua_mbar_arrive(kv_full + 8 * (t & 1));
         if (t + 1 < T) {
           const int s1 = (t + 1) & 1;
           if (t + 1 >= 2) ua_mbar_wait(kv_empty + 8 * s1, (((t + 1) >> 1) & 1) ^ 1);
           ua_stage<HDP>(sK + s1 * UA_TILE_BYTES, kb, rs, (t + 1) * UA_BN, N, hd, lane);
           ua_stage<HDP>(sV + s1 * UA_TILE_BYTES, vb, rs, (t + 1) * UA_BN, N, hd, lane);
           asm volatile("cp.async.commit_group;" ::: "memory");
-          asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-        ua_fence_async_smem();
-        ua_mbar_arrive(kv_full + 8 * (t & 1));
       }
     }
   } else if (warp == 1) {
@@ -352,15 +257,15 @@ typedef CUresult (*PFN_ua_encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// qkv [B, N, 3*H*hd] bf16 viewed as a 3-D tensor {cols, N, B}; box = {64 cols, 128 rows, 1}, SWIZZLE_128B.
-static int ua_qkv_map(const void* qkv, int B, int N, int cols, CUtensorMap* out) {
-  struct Key { const void* p; int B, N, cols; };
+// [B, N, cols] bf16 viewed as a 3-D tensor {cols, N, B}; box = {64 cols, box_rows rows, 1}, SWIZZLE_128B.
+int ua_make_map3d(const void* qkv, int B, int N, int cols, int box_rows, CUtensorMap* out) {
+  struct Key { const void* p; int B, N, cols, box_rows; };
   static std::mutex mu;
   static std::vector<std::pair<Key, CUtensorMap>> cache;
   {
     std::lock_guard<std::mutex> g(mu);
     for (auto& e : cache)
-      if (e.first.p == qkv && e.first.B == B && e.first.N == N && e.first.cols == cols) { *out = e.second; return 0; }
+      if (e.first.p == qkv && e.first.B == B && e.first.N == N && e.first.cols == cols && e.first.box_rows == box_rows) { *out = e.second; return 0; }
   }
   static PFN_ua_encode enc = nullptr;
   if (!enc) {
@@ -373,7 +278,7 @@ static int ua_qkv_map(const void* qkv, int B, int N, int cols, CUtensorMap* out)
   AVJ_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)N, (cuuint64_t)B};
   cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)cols * 2 * (cuuint64_t)N};
-  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -381,7 +286,7 @@ static int ua_qkv_map(const void* qkv, int B, int N, int cols, CUtensorMap* out)
   AVJ_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(qkv) failed (%d)", (int)r);
   std::lock_guard<std::mutex> g(mu);
   if (cache.size() > 512) cache.clear();
-  cache.push_back({Key{qkv, B, N, cols}, *out});
+  cache.push_back({Key{qkv, B, N, cols, box_rows}, *out});
   return 0;
 }
 
@@ -398,7 +303,7 @@ static int ua_launch(const bf16* qkv, bf16* out, float* lse, int B, int N, int H
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
   if (TMA) {
-    int rc = ua_qkv_map(qkv, B, N, 3 * H * hd, &map);
+    int rc = ua_make_map3d(qkv, B, N, 3 * H * hd, 128, &map);
     if (rc) return rc;
   }
   dim3 grid((N + UA_BM - 1) / UA_BM, H, B);

@@ -1,0 +1,352 @@
+// K7 flash-attention BACKWARD on the 5th-gen tensor cores (sm_100a), two deterministic passes built
+// from ONE kernel template (no atomics, no dQ accumulation buffer):
+//
+//   KV pass (KV = true ): CTA owns 128 keys of one (batch, head) and streams 64-query tiles
+//        S^T  = K Q^T          P^T  = exp2(S^T * scale*log2e - lse*log2e)      (TMEM lane = key)
+//        dP^T = V dO^T         dS^T = P^T o (dP^T - delta) * scale
+//        dV  += P^T dO         dK  += dS^T Q
+//   Q pass  (KV = false): CTA owns 128 queries and streams 64-key tiles
+//        S    = Q K^T          dP   = dO V^T                                   (TMEM lane = query)
+//        dS   = P o (dP - delta) * scale          dQ += dS K
+//
+// Computing the TRANSPOSED scores in the KV pass makes P^T / dS^T row-per-thread, so they are written to
+// shared memory as K-major A operands of the dV / dK MMAs with no transpose anywhere; the streamed
+// Q / dO (or K / V) tiles serve both as K-major B operands of the score MMAs and as MN-major B
+// operands of the output MMAs from the same shared-memory bytes.
+//
+//   warp 0      : loader (TMA box loads when hd == 64, else 16-byte cp.async gathers with zero padding
+//                 hd -> HDP in shared memory only) + per-column lse/delta staging for the KV pass
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer
+//   warps 2..5  : one thread per TMEM lane: tcgen05.ld of both 128x64 score tiles, exp2 / dS math in
+//                 fp32, bf16 pack, swizzled st.shared; final dK/dV (or dQ) TMEM -> bf16 -> dqkv
+//
+// TMEM: scores 2 x 64 columns + outputs 2 x HDP columns <= 256, so two CTAs share an SM and overlap
+// each other's MMA and exp2 phases.  Rows past N are zero (TMA OOB fill / explicit zero) which makes
+// every masked contribution vanish without predicates; lse/delta of such rows are staged as 0.
+//
+// Roofline: MUFU/FMA-bound like the forward (one exp2 + ~6 FMA-pipe ops per score element, twice --
+// once per pass).  Algorithmic FLOPs: 10 * N^2 * hd per (batch, head); executed: 14 * N^2 * HDP.
+#include "umma_attn.cuh"
+
+#include <mutex>
+#include <stdlib.h>
+#include <utility>
+#include <vector>
+
+#define UB_BM 128
+#define UB_BN 64
+#define UB_THREADS 192
+#define UB_ROW_TILE (128 * 128)      // 128 rows x 128 B
+#define UB_COL_TILE (64 * 128)       // 64 rows x 128 B
+#define UB_TMEM_COLS 256
+#define UB_T2_COL 64
+#define UB_O1_COL 128
+#define UB_O2_COL 192
+
+template <bool KV> struct UbSmem {
+  static constexpr uint32_t R1 = 0, R2 = UB_ROW_TILE, C1 = 2 * UB_ROW_TILE, C2 = C1 + 2 * UB_COL_TILE,
+                            DS = C2 + 2 * UB_COL_TILE, P = DS + UB_ROW_TILE,
+                            STAT = KV ? P + UB_ROW_TILE : P,            // [2 stages][lse2 64 | delta 64] floats
+                            BARS = STAT + (KV ? 1024 : 0), TOTAL = BARS + 128;
+};
+
+template <int HDP, bool TMA, bool KV>
+__global__ void __launch_bounds__(UB_THREADS, 2)
+fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_constant__ CUtensorMap map_qkv64,
+                   const __grid_constant__ CUtensorMap map_do, const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+                   const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv,
+                   int N, int H, int hd, float scale, float scale_log2) {
+  using L = UbSmem<KV>;
+  extern __shared__ __align__(1024) uint8_t ub_raw[];
+  const uint32_t base = ua_smem(ub_raw);
+  const uint32_t sR1 = base + L::R1, sR2 = base + L::R2, sC1 = base + L::C1, sC2 = base + L::C2;
+  const uint32_t sDS = base + L::DS, sP = base + L::P;
+  const uint32_t bars = base + L::BARS;
+  const uint32_t c_full = bars;             // [2]
+  const uint32_t c_empty = bars + 16;       // [2]
+  const uint32_t t_full = bars + 32;
+  const uint32_t t_free = bars + 40;
+  const uint32_t p_full = bars + 48;
+  const uint32_t o_done = bars + 56;
+  const uint32_t tmem_slot = bars + 64;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(ub_raw + L::BARS + 64);
+  float* stat = reinterpret_cast<float*>(ub_raw + L::STAT);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y, r0 = blockIdx.x * UB_BM;
+  const int64_t rs = 3 * (int64_t)H * hd;                    // qkv row stride (elements)
+  const int64_t os = (int64_t)H * hd;                        // out / dout row stride
+  const bf16* qb = qkv + (int64_t)b * N * rs + (int64_t)h * hd;
+  const bf16* kb = qb + (int64_t)H * hd;
+  const bf16* vb = kb + (int64_t)H * hd;
+  const bf16* dob = dout + (int64_t)b * N * os + (int64_t)h * hd;
+  const float* lse_bh = lse + ((int64_t)b * H + h) * N;
+  const float* delta_bh = delta + ((int64_t)b * H + h) * N;
+  const int T = (N + UB_BN - 1) / UB_BN;
+
+  if (threadIdx.x == 0) {
+    if (base & 1023u) __trap();
+    ua_mbar_init(c_full, TMA ? 1 : 32); ua_mbar_init(c_full + 8, TMA ? 1 : 32);
+    ua_mbar_init(c_empty, 1); ua_mbar_init(c_empty + 8, 1);
+    ua_mbar_init(t_full, 1); ua_mbar_init(t_free, 128); ua_mbar_init(p_full, 128); ua_mbar_init(o_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)UB_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  ua_fence_before();
+  __syncthreads();
+  ua_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ============================ loader ============================
+    // stationary tiles: KV pass K, V ; Q pass Q, dO.   streamed tiles: KV pass Q, dO ; Q pass K, V.
+    const int c_r1 = KV ? (H + h) * hd : h * hd;              // column of R1 inside a qkv row
+    const int c_c1 = KV ? h * hd : (H + h) * hd;
+    if (TMA && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv64) : "memory");
+    if (!TMA) {
+      ua_stage<HDP, 128>(sR1, KV ? kb : qb, rs, r0, N, hd, lane);
+      if (KV) ua_stage<HDP, 128>(sR2, vb, rs, r0, N, hd, lane);
+      else    ua_stage<HDP, 128>(sR2, dob, os, r0, N, hd, lane);
+    }
+    for (int t = 0; t < T; ++t) {
+      const int st = t & 1;
+      if (!TMA && t > 0) {
+        // tile t-1 has landed: signal it BEFORE waiting for stage `st` to drain -- the MMA warp issues
+        // scores(t-1) ahead of outputs(t-2), so the opposite order would deadlock.
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        ua_fence_async_smem();
+        ua_mbar_arrive(c_full + 8 * ((t - 1) & 1));
+      }
+      if (t >= 2) ua_mbar_wait(c_empty + 8 * st, ((t >> 1) & 1) ^ 1);
+      if (KV) {                                               // per-column statistics of this query tile
+        for (int i = lane; i < UB_BN; i += 32) {
+          const int qi = t * UB_BN + i;
+          stat[st * 128 + i] = qi < N ? lse_bh[qi] * 1.4426950408889634f : 0.f;
+          stat[st * 128 + 64 + i] = qi < N ? delta_bh[qi] : 0.f;
+        }
+        __syncwarp();
+      }
+      const uint32_t c1 = sC1 + st * UB_COL_TILE, c2 = sC2 + st * UB_COL_TILE;
+      if (TMA) {
+        if (lane == 0) {
+          const uint32_t fb = c_full + 8 * st;
+          ua_expect_tx(fb, 2 * UB_COL_TILE + (t == 0 ? 2 * UB_ROW_TILE : 0));
+          if (t == 0) {
+            ua_tma3d(sR1, &map_qkv128, fb, c_r1, r0, b);
+            if (KV) ua_tma3d(sR2, &map_qkv128, fb, (2 * H + h) * hd, r0, b);
+            else    ua_tma3d(sR2, &map_do, fb, h * hd, r0, b);
+          }
+          ua_tma3d(c1, &map_qkv64, fb, c_c1, t * UB_BN, b);
+          if (KV) ua_tma3d(c2, &map_do, fb, h * hd, t * UB_BN, b);
+          else    ua_tma3d(c2, &map_qkv64, fb, (2 * H + h) * hd, t * UB_BN, b);
+        }
+      } else {
+        ua_stage<HDP, 64>(c1, KV ? qb : kb, rs, t * UB_BN, N, hd, lane);
+        if (KV) ua_stage<HDP, 64>(c2, dob, os, t * UB_BN, N, hd, lane);
+        else    ua_stage<HDP, 64>(c2, vb, rs, t * UB_BN, N, hd, lane);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+    }
+    if (!TMA) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      ua_fence_async_smem();
+      ua_mbar_arrive(c_full + 8 * ((T - 1) & 1));
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      const uint32_t idesc_t = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UB_BN >> 3) << 17) | ((uint32_t)(UB_BM >> 4) << 24);
+      const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HDP >> 3) << 17) | ((uint32_t)(UB_BM >> 4) << 24);
+      const uint64_t r1d = ua_desc(sR1, 1, 64), r2d = ua_desc(sR2, 1, 64);
+      auto issue_scores = [&](int t) {
+        const uint64_t c1d = ua_desc(sC1 + (t & 1) * UB_COL_TILE, 1, 64);
+        const uint64_t c2d = ua_desc(sC2 + (t & 1) * UB_COL_TILE, 1, 64);
+#pragma unroll
+        for (int k = 0; k < HDP / 16; ++k) ua_mma(tmem, r1d + 2 * k, c1d + 2 * k, idesc_t, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < HDP / 16; ++k) ua_mma(tmem + UB_T2_COL, r2d + 2 * k, c2d + 2 * k, idesc_t, k > 0 ? 1u : 0u);
+        ua_commit(t_full);
+      };
+      ua_mbar_wait(c_full, 0);
+      ua_fence_after();
+      issue_scores(0);
+      for (int t = 0; t < T; ++t) {
+        if (t + 1 < T) {
+          ua_mbar_wait(c_full + 8 * ((t + 1) & 1), ((t + 1) >> 1) & 1);
+          ua_mbar_wait(t_free, t & 1);                       // both score tiles of step t are in registers
+          ua_fence_after();
+          issue_scores(t + 1);
+        }
+        ua_mbar_wait(p_full, t & 1);
+        ua_fence_after();
+        const uint32_t c1 = sC1 + (t & 1) * UB_COL_TILE, c2 = sC2 + (t & 1) * UB_COL_TILE;
+        const uint32_t accum0 = t > 0 ? 1u : 0u;
+        const uint64_t dsd = ua_desc(sDS, 1, 64);
+        const uint64_t c1m = ua_desc(c1, 512, 64);           // MN-major view: 16 rows = 2048 B per K step
+        if (KV) {
+          const uint64_t pd = ua_desc(sP, 1, 64);
+          const uint64_t c2m = ua_desc(c2, 512, 64);
+#pragma unroll
+          for (int k = 0; k < UB_BN / 16; ++k) ua_mma(tmem + UB_O1_COL, pd + 2 * k, c2m + 128 * k, idesc_o, (accum0 | (k > 0)) ? 1u : 0u);   // dV += P^T dO
+#pragma unroll
+          for (int k = 0; k < UB_BN / 16; ++k) ua_mma(tmem + UB_O2_COL, dsd + 2 * k, c1m + 128 * k, idesc_o, (accum0 | (k > 0)) ? 1u : 0u);  // dK += dS^T Q
+        } else {
+#pragma unroll
+          for (int k = 0; k < UB_BN / 16; ++k) ua_mma(tmem + UB_O1_COL, dsd + 2 * k, c1m + 128 * k, idesc_o, (accum0 | (k > 0)) ? 1u : 0u);  // dQ += dS K
+        }
+        ua_commit(o_done);
+        ua_commit(c_empty + 8 * (t & 1));
+      }
+    }
+  } else {
+    // ============================ score math ============================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                            // TMEM lane = stationary row in tile
+    const uint32_t t_1 = tmem + ((uint32_t)(q * 32) << 16);
+    const int ri = r0 + row;
+    float my_l2 = 0.f, my_dl = 0.f;
+    if (!KV && ri < N) { my_l2 = lse_bh[ri] * 1.4426950408889634f; my_dl = delta_bh[ri]; }
+    for (int t = 0; t < T; ++t) {
+      ua_mbar_wait(t_full, t & 1);
+      ua_fence_after();
+      float s[64], dp[64];
+      ua_ld32(t_1, s); ua_ld32(t_1 + 32, s + 32);
+      ua_ld32(t_1 + UB_T2_COL, dp); ua_ld32(t_1 + UB_T2_COL + 32, dp + 32);
+      ua_ld_wait();
+      ua_fence_before();
+      ua_mbar_arrive(t_free);
+      uint32_t pk_p[KV ? 32 : 1], pk_d[32];
+      const float* st_l2 = stat + (t & 1) * 128;
+      if (KV) ua_mbar_wait(c_full + 8 * (t & 1), (t >> 1) & 1);   // acquire the loader's lse/delta stores
+#pragma unroll
+      for (int j = 0; j < 64; j += 4) {
+        float l2[4], dl[4];
+        if constexpr (KV) {
+          const float4 a = *reinterpret_cast<const float4*>(st_l2 + j);
+          const float4 d = *reinterpret_cast<const float4*>(st_l2 + 64 + j);
+          l2[0] = a.x; l2[1] = a.y; l2[2] = a.z; l2[3] = a.w;
+          dl[0] = d.x; dl[1] = d.y; dl[2] = d.z; dl[3] = d.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { l2[e] = my_l2; dl[e] = my_dl; }
+        }
+        float p[4], ds[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          p[e] = ua_exp2(fmaf(s[j + e], scale_log2, -l2[e]));
+          ds[e] = p[e] * (dp[j + e] - dl[e]) * scale;
+        }
+        if constexpr (KV) { pk_p[j >> 1] = pack_bf16x2(p[0], p[1]); pk_p[(j >> 1) + 1] = pack_bf16x2(p[2], p[3]); }
+        pk_d[j >> 1] = pack_bf16x2(ds[0], ds[1]); pk_d[(j >> 1) + 1] = pack_bf16x2(ds[2], ds[3]);
+      }
+      if (t > 0) ua_mbar_wait(o_done, (t - 1) & 1);           // output MMAs of step t-1 done: P / dS smem is ours
+      ua_fence_after();
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {                           // 8 chunks of 8 streamed columns
+        const uint32_t off = row * 128 + ((c ^ (row & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + off), "r"(pk_d[4 * c]), "r"(pk_d[4 * c + 1]),
+                     "r"(pk_d[4 * c + 2]), "r"(pk_d[4 * c + 3]) : "memory");
+        if constexpr (KV)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + off), "r"(pk_p[4 * c]), "r"(pk_p[4 * c + 1]),
+                       "r"(pk_p[4 * c + 2]), "r"(pk_p[4 * c + 3]) : "memory");
+      }
+      ua_fence_async_smem();
+      ua_fence_before();
+      ua_mbar_arrive(p_full);
+    }
+    ua_mbar_wait(o_done, (T - 1) & 1);
+    ua_fence_after();
+    // dqkv row layout [3][H][hd]: slot 0 = dQ, 1 = dK, 2 = dV
+    bf16* drow = dqkv + ((int64_t)b * N + ri) * rs + (int64_t)h * hd;
+#pragma unroll
+    for (int o = 0; o < (KV ? 2 : 1); ++o) {
+      const int slot = KV ? (o == 0 ? 2 : 1) : 0;
+      const uint32_t t_o = t_1 + (o == 0 ? UB_O1_COL : UB_O2_COL);
+#pragma unroll
+      for (int c = 0; c < HDP; c += 32) {
+        float v[32];
+        ua_ld32(t_o + c, v);
+        ua_ld_wait();
+        if (ri < N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (c + j < hd) {
+              float v8[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v8[e] = v[j + e];
+              store8<bf16>(drow + (int64_t)slot * H * hd + c + j, v8);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  ua_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ua_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)UB_TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------
+int avj_attention_delta(const void* out, const void* dout, float* delta, int B, int N, int H, int hd, cudaStream_t s);
+int ua_make_map3d(const void* ptr, int B, int N, int cols, int box_rows, CUtensorMap* out);
+
+bool avj_attention_umma_bwd_supported(int dtype, int hd) {
+  return dtype == AVJ_BF16 && hd % 8 == 0 && hd >= 8 && hd <= 64;
+}
+
+template <int HDP, bool TMA, bool KV>
+static int ub_launch(const CUtensorMap& m128, const CUtensorMap& m64, const CUtensorMap& mdo, const bf16* qkv, const bf16* dout,
+                     const float* lse, const float* delta, bf16* dqkv, int B, int N, int H, int hd, float scale, cudaStream_t s) {
+  static bool set = false;
+  const int smem = (int)UbSmem<KV>::TOTAL;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(fa_bwd_umma_kernel<HDP, TMA, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    AVJ_CHECK(e == cudaSuccess, "cudaFuncSetAttribute(fa_bwd_umma_kernel) failed: %s", cudaGetErrorString(e));
+    cudaFuncSetAttribute(fa_bwd_umma_kernel<HDP, TMA, KV>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    set = true;
+  }
+  dim3 grid((N + UB_BM - 1) / UB_BM, H, B);
+  fa_bwd_umma_kernel<HDP, TMA, KV><<<grid, UB_THREADS, smem, s>>>(m128, m64, mdo, qkv, dout, lse, delta, dqkv, N, H, hd, scale,
+                                                                  scale * 1.4426950408889634f);
+  AVJ_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int HDP, bool TMA>
+static int ub_both(const bf16* qkv, const bf16* dout, const float* lse, const float* delta, bf16* dqkv,
+                   int B, int N, int H, int hd, float scale, cudaStream_t s) {
+  CUtensorMap m128, m64, mdo64, mdo128;
+  memset(&m128, 0, sizeof(m128)); memset(&m64, 0, sizeof(m64)); memset(&mdo64, 0, sizeof(mdo64)); memset(&mdo128, 0, sizeof(mdo128));
+  if (TMA) {
+    int rc;
+    if ((rc = ua_make_map3d(qkv, B, N, 3 * H * hd, 128, &m128))) return rc;
+    if ((rc = ua_make_map3d(qkv, B, N, 3 * H * hd, 64, &m64))) return rc;
+    if ((rc = ua_make_map3d(dout, B, N, H * hd, 64, &mdo64))) return rc;
+    if ((rc = ua_make_map3d(dout, B, N, H * hd, 128, &mdo128))) return rc;
+  }
+  int rc = ub_launch<HDP, TMA, true>(m128, m64, mdo64, qkv, dout, lse, delta, dqkv, B, N, H, hd, scale, s);
+  if (rc) return rc;
+  return ub_launch<HDP, TMA, false>(m128, m64, mdo128, qkv, dout, lse, delta, dqkv, B, N, H, hd, scale, s);
+}
+
+int avj_attention_bwd_umma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* ws,
+                           int B, int N, int H, int hd, float scale, cudaStream_t s) {
+  int rc = avj_attention_delta(out, dout, ws, B, N, H, hd, s);
+  if (rc) return rc;
+  static int use_tma = -1;
+  if (use_tma < 0) { const char* e = getenv("AVJ_ATTN_TMA"); use_tma = (e && e[0] == '0') ? 0 : 1; }
+  const bool aligned = ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(dout)) & 15) == 0;
+  if (hd <= 32) return ub_both<32, false>((const bf16*)qkv, (const bf16*)dout, lse, ws, (bf16*)dqkv, B, N, H, hd, scale, s);
+  if (hd == 64 && use_tma && aligned)
+    return ub_both<64, true>((const bf16*)qkv, (const bf16*)dout, lse, ws, (bf16*)dqkv, B, N, H, hd, scale, s);
+  return ub_both<64, false>((const bf16*)qkv, (const bf16*)dout, lse, ws, (bf16*)dqkv, B, N, H, hd, scale, s);
+}

@@ -22,6 +22,15 @@ int avj_attention_bwd_mma(const void* qkv, const void* out, const void* dout, co
 bool avj_attention_umma_fwd_supported(int dtype, int hd);
 int avj_attention_fwd_umma(const void* qkv, void* out, float* lse, int B, int N, int H, int hd, float scale, cudaStream_t s);
 
+bool avj_attention_umma_bwd_supported(int dtype, int hd);
+int avj_attention_bwd_umma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* ws,
+                           int B, int N, int H, int hd, float scale, cudaStream_t s);
+static bool attn_bwd_use_umma() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("AVJ_ATTN_BWD"); v = (e && e[0] == 'm') ? 0 : 1; }
+  return v == 1;
+}
+
 // AVJ_ATTN_FWD = umma (default) | mma : which tensor-core forward kernel serves bf16 attention
 static bool attn_fwd_use_umma() {
   static int v = -1;
@@ -80,6 +89,8 @@ extern "C" int avj_attention_bwd(int dtype, const void* qkv, const void* out, co
   AVJ_CHECK(hd > 0 && hd <= 128, "avj_attention_bwd: head_dim %d out of range (1..128)", hd);
   AVJ_CHECK(ws != nullptr, "avj_attention_bwd: workspace required");
   if (B == 0 || N == 0) return 0;
+  if (!force_simt_attn() && attn_bwd_use_umma() && avj_attention_umma_bwd_supported(dtype, hd))
+    return avj_attention_bwd_umma(qkv, out, dout, lse, dqkv, ws, B, N, H, hd, scale, as_stream(stream));
   if (!force_simt_attn() && avj_attention_mma_supported(dtype, hd))
     return avj_attention_bwd_mma(qkv, out, dout, lse, dqkv, ws, B, N, H, hd, scale, as_stream(stream));
   return avj_attention_bwd_simt(dtype, qkv, out, dout, lse, dqkv, ws, B, N, H, hd, scale, as_stream(stream));

@@ -29,7 +29,8 @@
 #define UG_B_STAGE_BYTES (UG_MAX_BN * UG_BK * 2)    // 32 KB
 #define UG_EPI_WARPS 8
 #define UG_THREADS (64 + 32 * UG_EPI_WARPS)
-#define UG_SMEM_BYTES (UG_STAGES * (UG_A_STAGE_BYTES + UG_B_STAGE_BYTES) + 1024 + 256)
+#define UG_EPI_STAGE_BYTES 4096                     // per epilogue warp: 32 rows x 32 fp32, swizzled
+#define UG_SMEM_BYTES (UG_STAGES * (UG_A_STAGE_BYTES + UG_B_STAGE_BYTES) + 1024 + 256 + UG_EPI_WARPS * UG_EPI_STAGE_BYTES)
 
 struct UmmaParams {
   int M, N, K, ldc;
@@ -107,6 +108,9 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void f4_add(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+
 // shared-memory matrix descriptor, SWIZZLE_128B, sm_100 version field = 1
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo16, uint32_t sbo16) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(lbo16 & 0x3FFF) << 16) | ((uint64_t)(sbo16 & 0x3FFF) << 32) |
@@ -130,6 +134,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const uint32_t tfull_bar = bars + 16 * UG_STAGES;     // [2]
   const uint32_t tempty_bar = tfull_bar + 16;           // [2]
   const uint32_t tmem_slot = tempty_bar + 16;           // u32
+  const uint32_t epi_stage = bars + 256;                // [UG_EPI_WARPS] x 4 KB transpose buffers
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -221,41 +226,117 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else {
     // ================= epilogue warps =================
-    // 8 warps: two per TMEM lane quarter, each taking half of the tile's columns.
+    // 8 warps: two per TMEM lane quarter, each taking half of the tile's columns, 32 columns at a
+    // time.  tcgen05.ld hands every thread ONE ROW (32 consecutive columns); storing that straight to
+    // global memory would touch 32 different cache lines per instruction, so each 32x32 block is
+    // transposed through a private 4 KB swizzled shared-memory buffer first: afterwards a warp
+    // instruction covers 4 rows x 128 contiguous bytes and every global access of the fused
+    // epilogue (bias, residual, positional rows, GELU aux, C) is fully coalesced.
     const int q = warp & 3;                          // TMEM lane quarter this warp may touch
-    const int half = (warp - 2) >> 2;
+    const int ew = warp - 2;
+    const int half = ew >> 2;
     const int c_lo = half * (p.block_n / 2), c_hi = c_lo + p.block_n / 2;
+    const uint32_t stg = epi_stage + ew * UG_EPI_STAGE_BYTES;
+    const int sub = lane >> 3, c4 = lane & 7;        // coalesced phase: row i*4+sub, float4 column c4
+    const avj_epilogue& ep = p.ep;
     uint32_t acc = 0, acc_phase = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
       const int tile = u / p.split_k;
       const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+      const int row_base = m_blk * UG_BM + q * 32;
+      int prow[8];                                   // physical C row of my 8 rows, -1 = past M
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = row_base + i * 4 + sub;
+        prow[i] = r < p.M ? (int)map_row(ep.out_map, r) : -1;
+      }
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
-      const int64_t row = (int64_t)m_blk * UG_BM + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * UG_MAX_BN;
-      const bool row_ok = row < p.M;
+      uint32_t raw[32];
+      tmem_ld32_issue(taddr + c_lo, raw);
       for (int c = c_lo; c < c_hi; c += 32) {
-        uint32_t raw[32];
-        tmem_ld32_issue(taddr + c, raw);
-        const int n0 = n_blk * p.block_n + c;
-        float add[32];
-        if (p.split_k == 1 && row_ok) epilogue_prefetch<32>(p.ep, p.C, p.ldc, p.N, row, n0, add);
         tmem_ld_wait();
-        float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-        if (row_ok) {
-          if (p.split_k > 1) {
-            float* out = reinterpret_cast<float*>(p.C) + map_row(p.ep.out_map, row) * (int64_t)p.ldc + n0;
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t dst = stg + lane * 128 + ((j ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(raw[4 * j]), "r"(raw[4 * j + 1]),
+                       "r"(raw[4 * j + 2]), "r"(raw[4 * j + 3]) : "memory");
+        }
+        if (c + 32 < c_hi) {
+          tmem_ld32_issue(taddr + c + 32, raw);      // next block is in flight while this one is stored
+        } else {
+          tc_fence_before();
+          mbar_arrive(tempty_bar + 8 * acc);         // accumulator drained: the MMA warp may reuse it
+        }
+        __syncwarp();
+        float4 v[8];
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) atomicAdd(reinterpret_cast<float4*>(out + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
-          } else {
-            epilogue_apply_store<TAct, 32, true>(p.ep, p.C, p.ldc, p.N, row, n0, v, add);
+        for (int i = 0; i < 8; ++i) {
+          const int rl = i * 4 + sub;
+          const uint32_t src = stg + rl * 128 + ((c4 ^ (rl & 7)) << 4);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(src) : "memory");
+        }
+        __syncwarp();
+        const int n = n_blk * p.block_n + c + c4 * 4;
+        if (p.split_k > 1) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (prow[i] >= 0)
+              atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (int64_t)prow[i] * p.ldc + n), v[i]);
+          continue;
+        }
+        // ---- addends that do not depend on the accumulator: issue all loads first
+        float4 add[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          add[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (prow[i] < 0) continue;
+          const int64_t off = (int64_t)prow[i] * p.ldc + n;
+          if (ep.residual) add[i] = ld_f4(ep.residual + off);
+          if (ep.pos) {
+            const int r = row_base + i * 4 + sub;
+            const int64_t pr = ep.pos_idx ? ep.pos_idx[r] : (int64_t)(r % ep.pos_rows);
+            f4_add(add[i], ld_f4(ep.pos + pr * (int64_t)p.N + n));
+          }
+          if (ep.accumulate) f4_add(add[i], ld_f4(reinterpret_cast<const float*>(p.C) + off));
+        }
+        uint2 aux[8];
+        if (ep.dact_aux) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            aux[i] = make_uint2(0u, 0u);
+            if (prow[i] >= 0)
+              aux[i] = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(ep.dact_aux) +
+                                                       (int64_t)(row_base + i * 4 + sub) * p.N + n);
           }
         }
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ep.bias) b4 = ld_f4(ep.bias + n);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (prow[i] < 0) continue;
+          float4 a = v[i];
+          f4_add(a, b4);
+          if (ep.act == 1) {
+            if (ep.pre_out)
+              *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.pre_out) + (int64_t)(row_base + i * 4 + sub) * p.N + n) =
+                  make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+            a.x = gelu_fwd<true>(a.x); a.y = gelu_fwd<true>(a.y); a.z = gelu_fwd<true>(a.z); a.w = gelu_fwd<true>(a.w);
+          }
+          if (ep.dact_aux) {
+            float x0, x1, x2, x3;
+            unpack_bf16x2(aux[i].x, x0, x1); unpack_bf16x2(aux[i].y, x2, x3);
+            a.x *= gelu_bwd<true>(x0); a.y *= gelu_bwd<true>(x1); a.z *= gelu_bwd<true>(x2); a.w *= gelu_bwd<true>(x3);
+          }
+          f4_add(a, add[i]);
+          const int64_t off = (int64_t)prow[i] * p.ldc + n;
+          if (ep.out_dtype == AVJ_F32)
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + off) = a;
+          else
+            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.C) + off) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+        }
       }
-      tc_fence_before();
-      mbar_arrive(tempty_bar + 8 * acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }

@@ -1,0 +1,103 @@
+// Whole-stack kernel schedules: the forward and backward of L pre-LN transformer blocks issued from
+// ONE C call (host-side native runtime; the per-kernel entry points stay available for tests).
+// Restates Block.forward / Attention.forward / MLP.forward of the reference
+// (src/models/utils/modules.py:114-120, :61-78, :30-36) as an explicit launch sequence:
+//
+//   fwd : LN1 -> qkv GEMM(+bias) -> attention -> proj GEMM(+bias,+x) -> LN2 -> fc1 GEMM(+bias,GELU,
+//         pre-activation stash) -> fc2 GEMM(+bias,+x1)
+//   bwd : the same chain reversed; weight gradients accumulate in place (C += epilogue), bias
+//         gradients are column sums, LayerNorm backward fuses the residual-gradient add and emits the
+//         compute-dtype copy that feeds the next dgrad/wgrad GEMMs.
+#include "common.cuh"
+
+#define RC(expr)            \
+  do {                      \
+    int rc__ = (expr);      \
+    if (rc__) return rc__;  \
+  } while (0)
+
+static inline avj_epilogue epi(int out_dtype) {
+  avj_epilogue e;
+  memset(&e, 0, sizeof(e));
+  e.out_dtype = out_dtype;
+  return e;
+}
+
+extern "C" int avj_stack_forward(const avj_stack* s, const avj_layer* L, void* stream) {
+  AVJ_CHECK(s && L, "avj_stack_forward: NULL argument");
+  const int R = s->B * s->N, D = s->D, Hd = s->hidden, cd = s->dtype;
+  AVJ_CHECK(s->H > 0 && D % s->H == 0, "avj_stack_forward: D=%d not divisible by heads=%d", D, s->H);
+  const int hd = D / s->H;
+  const float scale = 1.0f / sqrtf((float)hd);
+  for (int i = 0; i < s->L; ++i) {
+    const avj_layer& w = L[i];
+    RC(avj_layernorm_fwd(w.x, w.n1.w, w.n1.b, w.h1, cd, w.mean1, w.rstd1, R, D, w.n1.eps, stream));
+    avj_epilogue e = epi(cd);
+    e.bias = w.qkv.b;
+    RC(avj_gemm(cd, AVJ_GEMM_NT, w.h1, w.qkv.w, w.qkv_act, R, 3 * D, D, D, D, 3 * D, &e, stream));
+    RC(avj_attention_fwd(cd, w.qkv_act, w.o, w.lse, s->B, s->N, s->H, hd, scale, stream));
+    e = epi(AVJ_F32);
+    e.bias = w.proj.b; e.residual = w.x;
+    RC(avj_gemm(cd, AVJ_GEMM_NT, w.o, w.proj.w, w.x1, R, D, D, D, D, D, &e, stream));
+    RC(avj_layernorm_fwd(w.x1, w.n2.w, w.n2.b, w.h2, cd, w.mean2, w.rstd2, R, D, w.n2.eps, stream));
+    e = epi(cd);
+    e.bias = w.fc1.b; e.act = 1; e.pre_out = w.pre;
+    RC(avj_gemm(cd, AVJ_GEMM_NT, w.h2, w.fc1.w, w.act, R, Hd, D, D, D, Hd, &e, stream));
+    e = epi(AVJ_F32);
+    e.bias = w.fc2.b; e.residual = w.x1;
+    RC(avj_gemm(cd, AVJ_GEMM_NT, w.act, w.fc2.w, w.x_out, R, D, Hd, Hd, Hd, D, &e, stream));
+  }
+  return 0;
+}
+
+extern "C" int avj_stack_backward(const avj_stack* s, const avj_layer* L, const avj_stack_scratch* sc, void* stream) {
+  AVJ_CHECK(s && L && sc, "avj_stack_backward: NULL argument");
+  const int R = s->B * s->N, D = s->D, Hd = s->hidden, cd = s->dtype;
+  const int hd = D / s->H;
+  const float scale = 1.0f / sqrtf((float)hd);
+  const avj_rowmap ident = {0, 0, 0};
+  float* cur = sc->dxa;
+  float* nxt = sc->dxb;
+  for (int i = s->L - 1; i >= 0; --i) {
+    const avj_layer& w = L[i];
+    AVJ_CHECK(w.pre != nullptr, "avj_stack_backward: layer %d has no saved pre-activation (forward ran without save)", i);
+    // ---- MLP: x2 = x1 + fc2(gelu(fc1(LN2(x1))))
+    if (w.fc2.gb) RC(avj_colsum(sc->dx_lp, cd, D, ident, w.fc2.gb, R, D, sc->ws, stream));
+    avj_epilogue e;
+    if (w.fc2.gw) {
+      e = epi(AVJ_F32); e.accumulate = 1;
+      RC(avj_gemm(cd, AVJ_GEMM_TN, sc->dx_lp, w.act, w.fc2.gw, D, Hd, R, D, Hd, Hd, &e, stream));
+    }
+    e = epi(cd); e.dact_aux = w.pre;
+    RC(avj_gemm(cd, AVJ_GEMM_NN, sc->dx_lp, w.fc2.w, sc->d_hid, R, Hd, D, D, Hd, Hd, &e, stream));
+    if (w.fc1.gb) RC(avj_colsum(sc->d_hid, cd, Hd, ident, w.fc1.gb, R, Hd, sc->ws, stream));
+    if (w.fc1.gw) {
+      e = epi(AVJ_F32); e.accumulate = 1;
+      RC(avj_gemm(cd, AVJ_GEMM_TN, sc->d_hid, w.h2, w.fc1.gw, Hd, D, R, Hd, D, D, &e, stream));
+    }
+    e = epi(cd);
+    RC(avj_gemm(cd, AVJ_GEMM_NN, sc->d_hid, w.fc1.w, sc->d_h, R, D, Hd, Hd, D, D, &e, stream));
+    RC(avj_layernorm_bwd(sc->d_h, cd, w.x1, w.n2.w, w.mean2, w.rstd2, cur, nxt, sc->dx_lp, cd, w.n2.gw, w.n2.gb, sc->ws, R, D, stream));
+    { float* t = cur; cur = nxt; nxt = t; }
+    // ---- attention: x1 = x + proj(attn(qkv(LN1(x))))
+    if (w.proj.gb) RC(avj_colsum(sc->dx_lp, cd, D, ident, w.proj.gb, R, D, sc->ws, stream));
+    if (w.proj.gw) {
+      e = epi(AVJ_F32); e.accumulate = 1;
+      RC(avj_gemm(cd, AVJ_GEMM_TN, sc->dx_lp, w.o, w.proj.gw, D, D, R, D, D, D, &e, stream));
+    }
+    e = epi(cd);
+    RC(avj_gemm(cd, AVJ_GEMM_NN, sc->dx_lp, w.proj.w, sc->d_o, R, D, D, D, D, D, &e, stream));
+    RC(avj_attention_bwd(cd, w.qkv_act, w.o, sc->d_o, w.lse, sc->d_qkv, sc->ws, s->B, s->N, s->H, hd, scale, stream));
+    if (w.qkv.gb) RC(avj_colsum(sc->d_qkv, cd, 3 * D, ident, w.qkv.gb, R, 3 * D, sc->ws, stream));
+    if (w.qkv.gw) {
+      e = epi(AVJ_F32); e.accumulate = 1;
+      RC(avj_gemm(cd, AVJ_GEMM_TN, sc->d_qkv, w.h1, w.qkv.gw, 3 * D, D, R, 3 * D, D, D, &e, stream));
+    }
+    e = epi(cd);
+    RC(avj_gemm(cd, AVJ_GEMM_NN, sc->d_qkv, w.qkv.w, sc->d_h, R, D, 3 * D, 3 * D, D, D, &e, stream));
+    RC(avj_layernorm_bwd(sc->d_h, cd, w.x, w.n1.w, w.mean1, w.rstd1, cur, nxt, sc->dx_lp, cd, w.n1.gw, w.n1.gb, sc->ws, R, D, stream));
+    { float* t = cur; cur = nxt; nxt = t; }
+  }
+  // two swaps per layer: the result is back in dxa
+  return 0;
+}

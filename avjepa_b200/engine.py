@@ -276,11 +276,38 @@ class StackRun(object):
              act=1, pre_out=self.slot(i, 'pre') if self.save else None)
         gemm(m, GEMM_NT, self.slot(i, 'act'), w.fc2.w, xo, R, D, Hd, Hd, Hd, D, F32, bias=w.fc2.b, residual=x1)
 
+    # -- whole-stack C schedule --------------------------------------------------------------
+    def _stack_desc(self):
+        return _cabi.Stack(self.mode.code, self.B, self.N, self.D, self.H, self.Hd, self.L)
+
+    def _layer_array(self, blocks):
+        """ctypes array of avj_layer: weight pointers + this run's activation slots."""
+        arr = (_cabi.Layer * self.L)()
+        for i, w in enumerate(blocks):
+            l = arr[i]
+            for name in ('n1', 'n2'):
+                src, dst = getattr(w, name), getattr(l, name)
+                dst.w, dst.b, dst.gw, dst.gb, dst.eps = src.w, src.b, src.gw, src.gb, src.eps
+            for name in ('qkv', 'proj', 'fc1', 'fc2'):
+                src, dst = getattr(w, name), getattr(l, name)
+                dst.w, dst.b, dst.gw, dst.gb = src.w, src.b, src.gw, src.gb
+            sl = self.slot
+            l.x, l.x_out = self.x_in(i), self.x_out(i)
+            l.mean1, l.rstd1, l.h1, l.qkv_act, l.o, l.lse = (sl(i, 'mean1'), sl(i, 'rstd1'), sl(i, 'h1'), sl(i, 'qkv'),
+                                                            sl(i, 'o'), sl(i, 'lse'))
+            l.x1, l.mean2, l.rstd2, l.h2, l.act = sl(i, 'x1'), sl(i, 'mean2'), sl(i, 'rstd2'), sl(i, 'h2'), sl(i, 'act')
+            l.pre = sl(i, 'pre') if self.save else None
+        return arr
+
+    # kernels per layer issued by avj_stack_forward / avj_stack_backward (for the launch counter)
+    FWD_LAUNCHES_PER_LAYER = 7
+
     def forward(self, blocks, norm, out_ptr, out_dtype):
         """blocks: list[BlockW]; norm: NormW or None.  Writes LN(x_L) to out_ptr."""
         R, D = self.R, self.D
-        for i, w in enumerate(blocks):
-            self.forward_layer(i, w)
+        if self.L > 0:
+            desc, arr = self._stack_desc(), self._layer_array(blocks)
+            _cabi.call('avj_stack_forward', C.byref(desc), arr, stream(), launches=self.FWD_LAUNCHES_PER_LAYER * self.L)
         self.x_last = self.x_in(self.L)
         if norm is not None:
             layernorm_fwd(self.x_last, norm.w, norm.b, out_ptr, out_dtype, self.mean_f, self.rstd_f, R, D, norm.eps)
@@ -318,36 +345,11 @@ class StackRun(object):
         else:
             copy_rows(dy_ptr, dy_dtype, D, _cabi.IDENTITY, cur, F32, D, _cabi.IDENTITY, R, D)
             copy_rows(dy_ptr, dy_dtype, D, _cabi.IDENTITY, dx_lp, cd, D, _cabi.IDENTITY, R, D)
-        for i in reversed(range(self.L)):
-            w = blocks[i]
-            # ---- MLP: x2 = x1 + fc2(gelu(fc1(LN2(x1))))
-            if w.fc2.gb is not None:
-                colsum(dx_lp, cd, D, _cabi.IDENTITY, w.fc2.gb, R, D, ws)
-            if w.fc2.gw is not None:
-                gemm(m, GEMM_TN, dx_lp, self.slot(i, 'act'), w.fc2.gw, D, Hd, R, D, Hd, Hd, F32, accumulate=1)
-            gemm(m, GEMM_NN, dx_lp, w.fc2.w, d_hid, R, Hd, D, D, Hd, Hd, cd, dact_aux=self.slot(i, 'pre'))
-            if w.fc1.gb is not None:
-                colsum(d_hid, cd, Hd, _cabi.IDENTITY, w.fc1.gb, R, Hd, ws)
-            if w.fc1.gw is not None:
-                gemm(m, GEMM_TN, d_hid, self.slot(i, 'h2'), w.fc1.gw, Hd, D, R, Hd, D, D, F32, accumulate=1)
-            gemm(m, GEMM_NN, d_hid, w.fc1.w, d_h, R, D, Hd, Hd, D, D, cd)
-            layernorm_bwd(d_h, cd, self.slot(i, 'x1'), w.n2.w, self.slot(i, 'mean2'), self.slot(i, 'rstd2'), cur, nxt, dx_lp, cd,
-                          w.n2.gw, w.n2.gb, ws, R, D)
-            cur, nxt = nxt, cur
-            # ---- attention: x1 = x + proj(attn(qkv(LN1(x))))
-            if w.proj.gb is not None:
-                colsum(dx_lp, cd, D, _cabi.IDENTITY, w.proj.gb, R, D, ws)
-            if w.proj.gw is not None:
-                gemm(m, GEMM_TN, dx_lp, self.slot(i, 'o'), w.proj.gw, D, D, R, D, D, D, F32, accumulate=1)
-            gemm(m, GEMM_NN, dx_lp, w.proj.w, d_o, R, D, D, D, D, D, cd)
-            _cabi.call('avj_attention_bwd', cd, self.slot(i, 'qkv'), self.slot(i, 'o'), d_o, self.slot(i, 'lse'), d_qkv, ws,
-                       self.B, self.N, self.H, self.hd, scale, stream())
-            if w.qkv.gb is not None:
-                colsum(d_qkv, cd, 3 * D, _cabi.IDENTITY, w.qkv.gb, R, 3 * D, ws)
-            if w.qkv.gw is not None:
-                gemm(m, GEMM_TN, d_qkv, self.slot(i, 'h1'), w.qkv.gw, 3 * D, D, R, 3 * D, D, D, F32, accumulate=1)
-            gemm(m, GEMM_NN, d_qkv, w.qkv.w, d_h, R, D, 3 * D, 3 * D, D, D, cd)
-            layernorm_bwd(d_h, cd, self.slot(i, 'x'), w.n1.w, self.slot(i, 'mean1'), self.slot(i, 'rstd1'), cur, nxt, dx_lp, cd,
-                          w.n1.gw, w.n1.gb, ws, R, D)
-            cur, nxt = nxt, cur
+        if self.L > 0:
+            desc, arr = self._stack_desc(), self._layer_array(blocks)
+            scs = _cabi.StackScratch(cur, nxt, dx_lp, d_hid, d_qkv, d_h, d_o, ws)
+            w0 = blocks[0]
+            per_layer = 8 + 2 * sum(1 for g in (w0.fc2.gb, w0.fc1.gb, w0.proj.gb, w0.qkv.gb) if g is not None) \
+                + sum(1 for g in (w0.fc2.gw, w0.fc1.gw, w0.proj.gw, w0.qkv.gw) if g is not None) + 3
+            _cabi.call('avj_stack_backward', C.byref(desc), arr, C.byref(scs), stream(), launches=per_layer * self.L)
         return cur

@@ -181,6 +181,33 @@ int avj_cast(const float* in, void* out, int out_dtype, int64_t n, void* stream)
 /* stream-ordered zero fill of a raw device range (gradient / scatter targets). */
 int avj_memset_zero(void* ptr, int64_t nbytes, void* stream);
 
+/* ---- whole-stack schedules: L pre-LN transformer blocks (Block.forward / Attention.forward /
+ *      MLP.forward, src/models/utils/modules.py:114-120, :61-78, :30-36) issued as ONE call, so the
+ *      host pays one FFI crossing per stack instead of one per kernel.  Every pointer is caller
+ *      owned; activation slots are the per-layer buffers the backward re-reads (pre may be NULL in
+ *      a no-grad forward).  Gradient pointers (gw/gb) may be NULL (frozen parameter). */
+typedef struct avj_linear_w { const void* w; const float* b; float* gw; float* gb; } avj_linear_w;
+typedef struct avj_norm_w { const float* w; const float* b; float* gw; float* gb; float eps; int32_t pad_; } avj_norm_w;
+typedef struct avj_layer {
+  avj_norm_w n1; avj_linear_w qkv; avj_linear_w proj; avj_norm_w n2; avj_linear_w fc1; avj_linear_w fc2;
+  float* x; float* mean1; float* rstd1; void* h1; void* qkv_act; void* o; float* lse;
+  float* x1; float* mean2; float* rstd2; void* h2; void* pre; void* act;
+  float* x_out;            /* residual stream after this block (= next layer's x)          */
+} avj_layer;
+typedef struct avj_stack {
+  int32_t dtype;           /* AVJ_F32 / AVJ_BF16: operand dtype of GEMMs and attention      */
+  int32_t B, N, D, H, hidden, L;
+} avj_stack;
+typedef struct avj_stack_scratch {
+  float* dxa; float* dxb;  /* fp32 [B*N, D] residual-gradient ping/pong; dxa holds d x_L on entry
+                              and d x_0 on return                                            */
+  void* dx_lp;             /* compute-dtype copy of the current residual gradient (in/out)  */
+  void* d_hid; void* d_qkv; void* d_h; void* d_o;
+  float* ws;               /* max of the layernorm_bwd / colsum / attention_bwd workspaces  */
+} avj_stack_scratch;
+int avj_stack_forward(const avj_stack* s, const avj_layer* layers, void* stream);
+int avj_stack_backward(const avj_stack* s, const avj_layer* layers, const avj_stack_scratch* sc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

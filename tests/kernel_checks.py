@@ -161,7 +161,14 @@ def check_attention(code, B, N, H, hd, seed=0):
     ref.backward(dout.float())
     e_g = _rel(dqkv.float(), qf.grad)
     tol = 3e-2 if code == BF16 else 5e-5
-    return (e_o < tol and e_l < 1e-3 and e_g < tol), max(e_o, e_g)
+    global LAST_ATTENTION_ERRORS
+    LAST_ATTENTION_ERRORS = dict(out=e_o, lse=e_l, dq=_rel(dqkv[:, :, 0].float(), qf.grad[:, :, 0]),
+                                 dk=_rel(dqkv[:, :, 1].float(), qf.grad[:, :, 1]), dv=_rel(dqkv[:, :, 2].float(), qf.grad[:, :, 2]))
+    ok_parts = all(LAST_ATTENTION_ERRORS[k] < tol for k in ('dq', 'dk', 'dv'))
+    return (e_o < tol and e_l < 1e-3 and e_g < tol and ok_parts), max(e_o, e_g)
+
+
+LAST_ATTENTION_ERRORS = {}
 
 
 def check_gather(code, B=3, N=1568, K=300, D=192, seed=0):

@@ -101,6 +101,8 @@ PROTOTYPES = {
     'avj_clip_coef': (_i, [_vp, _f, _f, _vp, _vp]),
     'avj_cast': (_i, [_vp, _vp, _i, _i64, _vp]),
     'avj_memset_zero': (_i, [_vp, _i64, _vp]),
+    'avj_prof_enable': (_i, [_i]),
+    'avj_prof_collect': (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     'avj_stack_forward': (_i, [C.POINTER(Stack), C.POINTER(Layer), _vp]),
     'avj_stack_backward': (_i, [C.POINTER(Stack), C.POINTER(Layer), C.POINTER(StackScratch), _vp]),
 }
@@ -149,3 +151,20 @@ def call(name, *args, launches=1):
     lib = load()
     launch_count += launches
     check(getattr(lib, name)(*args), name)
+
+
+PROF_FAMILIES = ('gemm', 'attention_fwd', 'attention_bwd', 'layernorm_fwd', 'layernorm_bwd', 'colsum', 'optimizer')
+
+
+def prof_enable(on):
+    check(load().avj_prof_enable(1 if on else 0), 'avj_prof_enable')
+
+
+def prof_collect():
+    """{family: (ms, work, launches)} for the records since prof_enable(True)."""
+    out = {}
+    for i, name in enumerate(PROF_FAMILIES):
+        ms, work, n = C.c_double(0), C.c_double(0), C.c_int(0)
+        check(load().avj_prof_collect(i, C.byref(ms), C.byref(work), C.byref(n)), 'avj_prof_collect')
+        out[name] = (ms.value, work.value, n.value)
+    return out

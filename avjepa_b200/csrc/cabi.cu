@@ -4,6 +4,59 @@
 #include "common.cuh"
 
 #include <stdlib.h>
+#include <mutex>
+#include <vector>
+
+// ---- kernel timing ---------------------------------------------------------------------------
+bool g_avj_prof_on = false;
+namespace {
+struct ProfRec { cudaEvent_t a, b; int family; double work; };
+std::vector<ProfRec> g_prof;
+std::mutex g_prof_mu;
+thread_local int t_prof_open = -1;
+}  // namespace
+
+void avj_prof_begin(int family, double work, cudaStream_t s) {
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  if (t_prof_open >= 0) return;                    // nested entry point: the outer scope owns the record
+  ProfRec r;
+  r.family = family; r.work = work;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, s);
+  g_prof.push_back(r);
+  t_prof_open = (int)g_prof.size() - 1;
+}
+void avj_prof_end(cudaStream_t s) {
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  if (t_prof_open < 0) return;
+  cudaEventRecord(g_prof[t_prof_open].b, s);
+  t_prof_open = -1;
+}
+extern "C" int avj_prof_enable(int on) {
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  t_prof_open = -1;
+  g_avj_prof_on = on != 0;
+  return 0;
+}
+// Sums the records of one family (synchronises on their events).  Any output pointer may be NULL.
+extern "C" int avj_prof_collect(int family, double* ms, double* work, int* launches) {
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  double t = 0.0, w = 0.0;
+  int n = 0;
+  for (auto& r : g_prof) {
+    if (r.family != family) continue;
+    AVJ_CUDA(cudaEventSynchronize(r.b));
+    float e = 0.f;
+    AVJ_CUDA(cudaEventElapsedTime(&e, r.a, r.b));
+    t += e; w += r.work; ++n;
+  }
+  if (ms) *ms = t;
+  if (work) *work = w;
+  if (launches) *launches = n;
+  return 0;
+}
 
 int avj_gemm_simt(int dtype, int layout, const void* A, const void* B, void* C, int M, int N, int K,
                   int lda, int ldb, int ldc, const avj_epilogue& ep, cudaStream_t s);
@@ -62,6 +115,7 @@ extern "C" int avj_gemm(int dtype, int layout, const void* A, const void* B, voi
     AVJ_CHECK(ep.accumulate, "avj_gemm: K == 0 is only meaningful for accumulate epilogues");
     return 0;
   }
+  AvjProfScope prof(AVJ_FAM_GEMM, 2.0 * M * (double)N * K, stream);
   if (!force_simt() && avj_gemm_umma_supported(dtype, layout, A, B, M, N, K, lda, ldb, ep))
     return avj_gemm_umma(layout, A, B, C, M, N, K, lda, ldb, ldc, ep, as_stream(stream));
   return avj_gemm_simt(dtype, layout, A, B, C, M, N, K, lda, ldb, ldc, ep, as_stream(stream));
@@ -76,6 +130,7 @@ extern "C" int avj_attention_fwd(int dtype, const void* qkv, void* out, float* l
                                  int B, int N, int H, int hd, float scale, void* stream) {
   AVJ_CHECK(hd > 0 && hd <= 128, "avj_attention_fwd: head_dim %d out of range (1..128)", hd);
   if (B == 0 || N == 0) return 0;
+  AvjProfScope prof(AVJ_FAM_ATTN_FWD, 4.0 * B * H * (double)N * N * hd, stream);
   if (!force_simt_attn() && attn_fwd_use_umma() && avj_attention_umma_fwd_supported(dtype, hd))
     return avj_attention_fwd_umma(qkv, out, lse, B, N, H, hd, scale, as_stream(stream));
   if (!force_simt_attn() && avj_attention_mma_supported(dtype, hd))
@@ -89,6 +144,7 @@ extern "C" int avj_attention_bwd(int dtype, const void* qkv, const void* out, co
   AVJ_CHECK(hd > 0 && hd <= 128, "avj_attention_bwd: head_dim %d out of range (1..128)", hd);
   AVJ_CHECK(ws != nullptr, "avj_attention_bwd: workspace required");
   if (B == 0 || N == 0) return 0;
+  AvjProfScope prof(AVJ_FAM_ATTN_BWD, 10.0 * B * H * (double)N * N * hd, stream);
   if (!force_simt_attn() && attn_bwd_use_umma() && avj_attention_umma_bwd_supported(dtype, hd))
     return avj_attention_bwd_umma(qkv, out, dout, lse, dqkv, ws, B, N, H, hd, scale, as_stream(stream));
   if (!force_simt_attn() && avj_attention_mma_supported(dtype, hd))

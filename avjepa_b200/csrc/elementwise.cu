@@ -265,6 +265,7 @@ extern "C" int avj_colsum(const void* in, int in_dtype, int ld, avj_rowmap map, 
                           int rows, int D, float* ws, void* stream) {
   AVJ_CHECK(D % 8 == 0 && ld % 8 == 0, "avj_colsum: D/ld must be multiples of 8");
   if (rows == 0 || D == 0) return 0;
+  AvjProfScope prof(AVJ_FAM_COLSUM, (double)rows * D * (in_dtype == AVJ_BF16 ? 2 : 4), stream);
   const int slabs = (rows + COLSUM_SLAB - 1) / COLSUM_SLAB;
   dim3 grid((D + 255) / 256, slabs), block(32, 8);
   if (in_dtype == AVJ_BF16)
@@ -451,6 +452,8 @@ extern "C" int avj_adamw_ema_step(const avj_adamw_args* a, void* stream) {
   AVJ_CHECK(a->skip_update || (a->g && a->m && a->v), "avj_adamw_ema_step: g/m/v required");
   const double bc1 = 1.0 - pow((double)a->beta1, (double)a->step);
   const double bc2 = 1.0 - pow((double)a->beta2, (double)a->step);
+  AvjProfScope prof(AVJ_FAM_OPTIM, (double)a->n * (a->skip_update ? 0 : 28) + (double)a->n * (a->target ? 8 : 0) +
+                                       (double)a->n * (a->zero_grad ? 4 : 0) + (double)a->n * ((a->p_lp ? 2 : 0) + (a->target_lp ? 2 : 0)), stream);
   const int grid = grid_for(a->n / 4, 256, 8);
   adamw_ema_kernel<<<grid, 256, 0, as_stream(stream)>>>(*a, (float)bc1, (float)sqrt(bc2));
   AVJ_LAUNCH_CHECK();

@@ -40,6 +40,7 @@ struct UmmaParams {
   int split_k;           // >= 1
   int kb_per_split;
   int a_mn_major, b_mn_major;
+  int epi_transposed;    // 1: 32x32 blocks go through the smem transpose (coalesced global access)
   uint32_t mn_lbo, mn_sbo, mn_kadv;   // MN-major descriptor fields / k-advance (16 B units)
   void* C;
   avj_epilogue ep;
@@ -108,6 +109,9 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void f4_add(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 
@@ -239,23 +243,96 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const uint32_t stg = epi_stage + ew * UG_EPI_STAGE_BYTES;
     const int sub = lane >> 3, c4 = lane & 7;        // coalesced phase: row i*4+sub, float4 column c4
     const avj_epilogue& ep = p.ep;
+    // Everything the epilogue ADDS comes from HBM (fp32 residual stream, previous C of a `C +=`, the saved
+    // pre-activation of GELU').  Those loads would each pay a full DRAM round trip in the middle of the
+    // epilogue, so the rows of the NEXT tile are pulled into L2 with bulk prefetches while this tile's
+    // MMAs are still running.
+    const bool want_pf = (ep.residual != nullptr) || (ep.dact_aux != nullptr) || (ep.accumulate && p.split_k == 1);
+    auto prefetch_tile = [&](int u) {
+      const int tile = u / p.split_k;
+      const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+      const int r = m_blk * UG_BM + q * 32 + lane;
+      if (r >= p.M) return;
+      const int n0 = n_blk * p.block_n + c_lo;
+      const uint32_t cols = (uint32_t)(p.block_n / 2);
+      const int64_t off = map_row(ep.out_map, r) * (int64_t)p.ldc + n0;
+      if (ep.residual) l2_prefetch(ep.residual + off, cols * 4);
+      if (ep.accumulate && p.split_k == 1) l2_prefetch(reinterpret_cast<const float*>(p.C) + off, cols * 4);
+      if (ep.dact_aux) l2_prefetch(reinterpret_cast<const bf16*>(ep.dact_aux) + (int64_t)r * p.N + n0, cols * 2);
+    };
+    if (want_pf && (int)blockIdx.x < n_units) prefetch_tile(blockIdx.x);
     uint32_t acc = 0, acc_phase = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
       const int tile = u / p.split_k;
       const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
       const int row_base = m_blk * UG_BM + q * 32;
+      if (want_pf && u + (int)gridDim.x < n_units) prefetch_tile(u + gridDim.x);
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * UG_MAX_BN;
+      uint32_t raw[32];
+      tmem_ld32_issue(taddr + c_lo, raw);
+
+      if (!p.epi_transposed) {
+        // ---------------- direct: thread == row, 32 consecutive columns per step ----------------
+        const int64_t row = row_base + lane;
+        const bool row_ok = row < p.M;
+        for (int c = c_lo; c < c_hi; c += 32) {
+          const int n0 = n_blk * p.block_n + c;
+          float add[32];
+          if (p.split_k == 1 && row_ok) epilogue_prefetch<32>(ep, p.C, p.ldc, p.N, row, n0, add);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+          if (c + 32 < c_hi) {
+            tmem_ld32_issue(taddr + c + 32, raw);
+          } else {
+            tc_fence_before();
+            mbar_arrive(tempty_bar + 8 * acc);
+          }
+          if (row_ok) {
+            if (p.split_k > 1) {
+              float* out = reinterpret_cast<float*>(p.C) + map_row(ep.out_map, row) * (int64_t)p.ldc + n0;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) atomicAdd(reinterpret_cast<float4*>(out + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+            } else {
+              epilogue_apply_store<TAct, 32, true>(ep, p.C, p.ldc, p.N, row, n0, v, add);
+            }
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
+
+      // ---------------- transposed: coalesced 4 rows x 128 B per warp instruction ----------------
       int prow[8];                                   // physical C row of my 8 rows, -1 = past M
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = row_base + i * 4 + sub;
         prow[i] = r < p.M ? (int)map_row(ep.out_map, r) : -1;
       }
-      mbar_wait(tfull_bar + 8 * acc, acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * UG_MAX_BN;
-      uint32_t raw[32];
-      tmem_ld32_issue(taddr + c_lo, raw);
       for (int c = c_lo; c < c_hi; c += 32) {
+        const int n = n_blk * p.block_n + c + c4 * 4;
+        // ---- addends that do not depend on the accumulator: issue all loads before the TMEM wait
+        float4 add[8];
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.split_k == 1) {
+          if (ep.bias) b4 = ld_f4(ep.bias + n);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            add[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (prow[i] < 0) continue;
+            const int64_t off = (int64_t)prow[i] * p.ldc + n;
+            if (ep.residual) add[i] = ld_f4(ep.residual + off);
+            if (ep.pos) {
+              const int r = row_base + i * 4 + sub;
+              const int64_t pr = ep.pos_idx ? ep.pos_idx[r] : (int64_t)(r % ep.pos_rows);
+              f4_add(add[i], ld_f4(ep.pos + pr * (int64_t)p.N + n));
+            }
+            if (ep.accumulate) f4_add(add[i], ld_f4(reinterpret_cast<const float*>(p.C) + off));
+          }
+        }
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -278,28 +355,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(src) : "memory");
         }
         __syncwarp();
-        const int n = n_blk * p.block_n + c + c4 * 4;
         if (p.split_k > 1) {
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             if (prow[i] >= 0)
               atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (int64_t)prow[i] * p.ldc + n), v[i]);
           continue;
-        }
-        // ---- addends that do not depend on the accumulator: issue all loads first
-        float4 add[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          add[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (prow[i] < 0) continue;
-          const int64_t off = (int64_t)prow[i] * p.ldc + n;
-          if (ep.residual) add[i] = ld_f4(ep.residual + off);
-          if (ep.pos) {
-            const int r = row_base + i * 4 + sub;
-            const int64_t pr = ep.pos_idx ? ep.pos_idx[r] : (int64_t)(r % ep.pos_rows);
-            f4_add(add[i], ld_f4(ep.pos + pr * (int64_t)p.N + n));
-          }
-          if (ep.accumulate) f4_add(add[i], ld_f4(reinterpret_cast<const float*>(p.C) + off));
         }
         uint2 aux[8];
         if (ep.dact_aux) {
@@ -311,8 +372,6 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                                                        (int64_t)(row_base + i * 4 + sub) * p.N + n);
           }
         }
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ep.bias) b4 = ld_f4(ep.bias + n);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           if (prow[i] < 0) continue;
@@ -469,6 +528,11 @@ int avj_gemm_umma(int layout, const void* A, const void* B, void* C, int M, int 
   }
   p.kb_per_split = (p.k_blocks + p.split_k - 1) / p.split_k;
   p.split_k = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;   // drop empty splits
+
+  // fp32 outputs (residual stream, weight gradients) take the smem-transposed coalesced epilogue; bf16
+  // outputs write 64 contiguous bytes per thread already and skip the extra shared-memory round trip.
+  static const uint32_t epi_mode = env_u32("AVJ_EPI_MODE", 0);      // 0 auto, 1 direct, 2 transposed
+  p.epi_transposed = epi_mode == 0 ? (ep.out_dtype == AVJ_F32) : (epi_mode == 2);
 
   CUtensorMap ma, mb;
   int rc;

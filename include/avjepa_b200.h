@@ -181,6 +181,13 @@ int avj_cast(const float* in, void* out, int out_dtype, int64_t n, void* stream)
 /* stream-ordered zero fill of a raw device range (gradient / scatter targets). */
 int avj_memset_zero(void* ptr, int64_t nbytes, void* stream);
 
+/* ---- in-library kernel timing (measurement only): while enabled, every GEMM / attention / LayerNorm /
+ *      column-sum / optimizer entry point brackets its launches with CUDA events on its stream.
+ *      avj_prof_collect sums one family: 0 gemm (work = FLOPs), 1 attention fwd, 2 attention bwd (FLOPs),
+ *      3 layernorm fwd, 4 layernorm bwd, 5 colsum, 6 optimizer (work = algorithmic bytes). */
+int avj_prof_enable(int on);
+int avj_prof_collect(int family, double* ms, double* work, int* launches);
+
 /* ---- whole-stack schedules: L pre-LN transformer blocks (Block.forward / Attention.forward /
  *      MLP.forward, src/models/utils/modules.py:114-120, :61-78, :30-36) issued as ONE call, so the
  *      host pays one FFI crossing per stack instead of one per kernel.  Every pointer is caller

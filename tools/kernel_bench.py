@@ -17,7 +17,12 @@ PEAKS = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.ex
     else dict(bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, hbm_gbs=6650.0)
 
 
-def timeit(fn, iters=20, warm=3):
+ITERS, WARM, WITH_LIBRARY = 20, 3, True     # tools/ncu_cases.py shrinks these for profiler captures
+
+
+def timeit(fn, iters=None, warm=None):
+    iters = ITERS if iters is None else iters
+    warm = WARM if warm is None else warm
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -65,6 +70,8 @@ def bench_gemm(layout, M, N, K, epi='none', tag=''):
     tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
     print(json.dumps(dict(kernel='gemm_umma', tag=tag, layout=['NT', 'NN', 'TN'][layout], M=M, N=N, K=K, epi=epi, ms=round(ms, 4),
                           tflops=round(tf, 1), frac_burst=round(tf / PEAKS['bf16_tflops'], 3))), flush=True)
+    if not WITH_LIBRARY:
+        return
     # cuBLAS (library) on the same shape, for context only
     A, B_ = As[0], Bs[0]
     Af = A.t() if layout == GEMM_TN else A
@@ -91,6 +98,8 @@ def bench_attn(B, N, H, hd, tag=''):
                           frac_burst=round(ff / ms_f / 1e9 / PEAKS['bf16_tflops'], 3))), flush=True)
     print(json.dumps(dict(kernel='fa_bwd(dq+dkv)', tag=tag, ms=round(ms_b, 4), tflops_alg10=round(2.5 * ff / ms_b / 1e9, 1),
                           tflops_exec14=round(3.5 * ff / ms_b / 1e9, 1))), flush=True)
+    if not WITH_LIBRARY:
+        return
     q, k, v = qkv.permute(2, 0, 3, 1, 4)
     ms_t = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v))
     print(json.dumps(dict(kernel='torch SDPA fwd (library)', tag=tag, ms=round(ms_t, 4), tflops=round(ff / ms_t / 1e9, 1))), flush=True)

@@ -2,11 +2,13 @@
 // tcgen05.mma instructions with their accumulators in TMEM; softmax runs on 128 threads that each own
 // one query row (= one TMEM lane).
 //
-//   warp 0      : loader -- cp.async 16-byte copies of Q / K / V head slices straight out of the
-//                 qkv-Linear output [B, N, 3, H, hd] into SWIZZLE_128B shared-memory tiles (zero
-//                 padding of hd -> HDP and of rows >= N happens here, in shared memory only)
+//   warp 0      : loader -- TMA box loads (hd == 64) or cp.async 16-byte copies of Q / K / V head slices
+//                 straight out of the qkv-Linear output [B, N, 3, H, hd] into SWIZZLE_128B shared-memory
+//                 tiles (zero padding of hd -> HDP and of rows >= N happens here, in shared memory only;
+//                 warps 2-3 help on the cp.async path)
 //   warp 1      : TMEM allocator + single-thread MMA issuer
-//   warps 2..5  : softmax: tcgen05.ld S (128 fp32 columns per row), running max / sum in fp32 with
+//   warps 4..7  : softmax (208 registers after setmaxnreg; warps 0-3 drop to 48 so that two CTAs fit the
+//                 register file of every SM sub-partition): tcgen05.ld S (128 fp32 columns per row), running max / sum in fp32 with
 //                 exp2f, P -> bf16 -> swizzled smem (A operand of the PV MMA), lazy rescale of the
 //                 TMEM-resident O only when a row maximum moves by more than 2^8, final O / l
 //
@@ -27,7 +29,8 @@
 
 #define UA_BM 128
 #define UA_BN 128
-#define UA_THREADS 192
+#define UA_THREADS 256
+#define UA_LOADERS 96             // cp.async path: warps 0, 2, 3
 #define UA_TILE_BYTES (128 * 128)                 // 128 rows x 128 B (one swizzle atom wide)
 #define UA_SMEM_BYTES (UA_TILE_BYTES * (1 + 2 + 2 + 2) + 256)   // Q, K[2], V[2], P(2 atoms) + barriers
 #define UA_TMEM_COLS 256
@@ -65,7 +68,7 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
 
   if (threadIdx.x == 0) {
     if (base & 1023u) __trap();                      // SWIZZLE_128B tiles need 1024-byte alignment
-    ua_mbar_init(kv_full, TMA ? 1 : 32); ua_mbar_init(kv_full + 8, TMA ? 1 : 32);
+    ua_mbar_init(kv_full, TMA ? 1 : UA_LOADERS); ua_mbar_init(kv_full + 8, TMA ? 1 : UA_LOADERS);
     ua_mbar_init(kv_empty, 1); ua_mbar_init(kv_empty + 8, 1);
     ua_mbar_init(s_full, 1); ua_mbar_init(s_free, 128); ua_mbar_init(p_full, 128); ua_mbar_init(o_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -79,8 +82,11 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
   ua_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
 
-  if (warp == 0) {
+  if (warp < 4) {
+  ua_reg_dec<48>();
+  if (warp == 0 || (!TMA && warp >= 2)) {
     // ============================ loader ============================
+    const int ld_tid = warp == 0 ? lane : (warp - 1) * 32 + lane;     // 0..95 on the cp.async path
     if (TMA) {
       if (lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
@@ -98,9 +104,9 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
     } else {
       // gather tile t+1 while the tensor core works on tile t.  kv_full[t] must be signalled BEFORE
       // waiting for the stage of tile t+1 to drain (the MMA warp issues S(t+1) ahead of PV(t)).
-      ua_stage<HDP>(sQ, qb, rs, q0, N, hd, lane);
-      ua_stage<HDP>(sK, kb, rs, 0, N, hd, lane);
-      ua_stage<HDP>(sV, vb, rs, 0, N, hd, lane);
+      ua_stage<HDP>(sQ, qb, rs, q0, N, hd, ld_tid, UA_LOADERS);
+      ua_stage<HDP>(sK, kb, rs, 0, N, hd, ld_tid, UA_LOADERS);
+      ua_stage<HDP>(sV, vb, rs, 0, N, hd, ld_tid, UA_LOADERS);
       asm volatile("cp.async.commit_group;" ::: "memory");
       for (int t = 0; t < T; ++t) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -109,8 +115,8 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
         if (t + 1 < T) {
           const int s1 = (t + 1) & 1;
           if (t + 1 >= 2) ua_mbar_wait(kv_empty + 8 * s1, (((t + 1) >> 1) & 1) ^ 1);
-          ua_stage<HDP>(sK + s1 * UA_TILE_BYTES, kb, rs, (t + 1) * UA_BN, N, hd, lane);
-          ua_stage<HDP>(sV + s1 * UA_TILE_BYTES, vb, rs, (t + 1) * UA_BN, N, hd, lane);
+          ua_stage<HDP>(sK + s1 * UA_TILE_BYTES, kb, rs, (t + 1) * UA_BN, N, hd, ld_tid, UA_LOADERS);
+          ua_stage<HDP>(sV + s1 * UA_TILE_BYTES, vb, rs, (t + 1) * UA_BN, N, hd, ld_tid, UA_LOADERS);
           asm volatile("cp.async.commit_group;" ::: "memory");
         }
       }
@@ -150,7 +156,9 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
         ua_commit(kv_empty + 8 * (t & 1));
       }
     }
+  }
   } else {
+    ua_reg_inc<208>();
     // ============================ softmax ============================
     const int q = warp & 3;
     const int row = q * 32 + lane;                                   // TMEM lane == query row in tile

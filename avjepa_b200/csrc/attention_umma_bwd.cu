@@ -15,10 +15,15 @@
 // operands of the output MMAs from the same shared-memory bytes.
 //
 //   warp 0      : loader (TMA box loads when hd == 64, else 16-byte cp.async gathers with zero padding
-//                 hd -> HDP in shared memory only) + per-column lse/delta staging for the KV pass
+//                 hd -> HDP in shared memory only; warps 2-3 help gathering) + per-column lse/delta
+//                 staging for the KV pass
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer
-//   warps 2..5  : one thread per TMEM lane: tcgen05.ld of both 128x64 score tiles, exp2 / dS math in
+//   warps 4..7  : one thread per TMEM lane: tcgen05.ld of both 128x64 score tiles, exp2 / dS math in
 //                 fp32, bf16 pack, swizzled st.shared; final dK/dV (or dQ) TMEM -> bf16 -> dqkv
+//
+// 256 threads compiled for 128 registers so that two CTAs are co-resident in EVERY SM sub-partition's
+// register file; warps 0-3 then shrink to 56 registers (setmaxnreg.dec) and the math warpgroup grows
+// to 200 (setmaxnreg.inc) -- it holds two 64-column fp32 score rows per thread.
 //
 // TMEM: scores 2 x 64 columns + outputs 2 x HDP columns <= 256, so two CTAs share an SM and overlap
 // each other's MMA and exp2 phases.  Rows past N are zero (TMA OOB fill / explicit zero) which makes
@@ -35,7 +40,8 @@
 
 #define UB_BM 128
 #define UB_BN 64
-#define UB_THREADS 192
+#define UB_THREADS 256
+#define UB_LOADERS 96            // cp.async path: warps 0, 2, 3
 #define UB_ROW_TILE (128 * 128)      // 128 rows x 128 B
 #define UB_COL_TILE (64 * 128)       // 64 rows x 128 B
 #define UB_TMEM_COLS 256
@@ -86,7 +92,7 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
 
   if (threadIdx.x == 0) {
     if (base & 1023u) __trap();
-    ua_mbar_init(c_full, TMA ? 1 : 32); ua_mbar_init(c_full + 8, TMA ? 1 : 32);
+    ua_mbar_init(c_full, TMA ? 1 : UB_LOADERS); ua_mbar_init(c_full + 8, TMA ? 1 : UB_LOADERS);
     ua_mbar_init(c_empty, 1); ua_mbar_init(c_empty + 8, 1);
     ua_mbar_init(t_full, 1); ua_mbar_init(t_free, 128); ua_mbar_init(p_full, 128); ua_mbar_init(o_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -100,16 +106,20 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
   ua_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
 
-  if (warp == 0) {
+  if (warp < 4) {
+  ua_reg_dec<56>();
+  if (warp == 0 || (!TMA && (warp == 2 || warp == 3))) {
     // ============================ loader ============================
+    const int ld_tid = warp == 0 ? lane : (warp - 1) * 32 + lane;     // 0..95 on the cp.async path
+    const int ld_n = TMA ? 32 : UB_LOADERS;
     // stationary tiles: KV pass K, V ; Q pass Q, dO.   streamed tiles: KV pass Q, dO ; Q pass K, V.
     const int c_r1 = KV ? (H + h) * hd : h * hd;              // column of R1 inside a qkv row
     const int c_c1 = KV ? h * hd : (H + h) * hd;
     if (TMA && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv64) : "memory");
     if (!TMA) {
-      ua_stage<HDP, 128>(sR1, KV ? kb : qb, rs, r0, N, hd, lane);
-      if (KV) ua_stage<HDP, 128>(sR2, vb, rs, r0, N, hd, lane);
-      else    ua_stage<HDP, 128>(sR2, dob, os, r0, N, hd, lane);
+      ua_stage<HDP, 128>(sR1, KV ? kb : qb, rs, r0, N, hd, ld_tid, ld_n);
+      if (KV) ua_stage<HDP, 128>(sR2, vb, rs, r0, N, hd, ld_tid, ld_n);
+      else    ua_stage<HDP, 128>(sR2, dob, os, r0, N, hd, ld_tid, ld_n);
     }
     for (int t = 0; t < T; ++t) {
       const int st = t & 1;
@@ -122,7 +132,7 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
       }
       if (t >= 2) ua_mbar_wait(c_empty + 8 * st, ((t >> 1) & 1) ^ 1);
       if (KV) {                                               // per-column statistics of this query tile
-        for (int i = lane; i < UB_BN; i += 32) {
+        for (int i = ld_tid; i < UB_BN; i += ld_n) {
           const int qi = t * UB_BN + i;
           stat[st * 128 + i] = qi < N ? lse_bh[qi] * 1.4426950408889634f : 0.f;
           stat[st * 128 + 64 + i] = qi < N ? delta_bh[qi] : 0.f;
@@ -144,9 +154,9 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
           else    ua_tma3d(c2, &map_qkv64, fb, (2 * H + h) * hd, t * UB_BN, b);
         }
       } else {
-        ua_stage<HDP, 64>(c1, KV ? qb : kb, rs, t * UB_BN, N, hd, lane);
-        if (KV) ua_stage<HDP, 64>(c2, dob, os, t * UB_BN, N, hd, lane);
-        else    ua_stage<HDP, 64>(c2, vb, rs, t * UB_BN, N, hd, lane);
+        ua_stage<HDP, 64>(c1, KV ? qb : kb, rs, t * UB_BN, N, hd, ld_tid, ld_n);
+        if (KV) ua_stage<HDP, 64>(c2, dob, os, t * UB_BN, N, hd, ld_tid, ld_n);
+        else    ua_stage<HDP, 64>(c2, vb, rs, t * UB_BN, N, hd, ld_tid, ld_n);
         asm volatile("cp.async.commit_group;" ::: "memory");
       }
     }
@@ -201,7 +211,9 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
         ua_commit(c_empty + 8 * (t & 1));
       }
     }
+  }
   } else {
+    ua_reg_inc<200>();
     // ============================ score math ============================
     const int q = warp & 3;
     const int row = q * 32 + lane;                            // TMEM lane = stationary row in tile

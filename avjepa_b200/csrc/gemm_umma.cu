@@ -28,7 +28,7 @@
 #define UG_A_STAGE_BYTES (UG_BM * UG_BK * 2)        // 16 KB
 #define UG_B_STAGE_BYTES (UG_MAX_BN * UG_BK * 2)    // 32 KB
 #define UG_EPI_WARPS 8
-#define UG_THREADS (64 + 32 * UG_EPI_WARPS)
+#define UG_THREADS (128 + 32 * UG_EPI_WARPS)   // warpgroup 0: producer, MMA, 2 idle; warpgroups 1-2: epilogue
 #define UG_EPI_STAGE_BYTES 4096                     // per epilogue warp: 32 rows x 32 fp32, swizzled
 #define UG_SMEM_BYTES (UG_STAGES * (UG_A_STAGE_BYTES + UG_B_STAGE_BYTES) + 1024 + 256 + UG_EPI_WARPS * UG_EPI_STAGE_BYTES)
 
@@ -40,7 +40,6 @@ struct UmmaParams {
   int split_k;           // >= 1
   int kb_per_split;
   int a_mn_major, b_mn_major;
-  int epi_transposed;    // 1: 32x32 blocks go through the smem transpose (coalesced global access)
   uint32_t mn_lbo, mn_sbo, mn_kadv;   // MN-major descriptor fields / k-advance (16 B units)
   void* C;
   avj_epilogue ep;
@@ -124,7 +123,28 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo16, ui
 // ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
-template <typename TAct>
+// Epilogue specialisations (compile-time, so the hot loop carries no dead registers or branches):
+//   EPI_PLAIN      thread == row, acc (+bias) -> bf16/fp32                       (qkv fprop, dgrads)
+//   EPI_GELU       + GELU, optional bf16 pre-activation stash                    (fc1 fprop)
+//   EPI_DACT       acc * GELU'(saved pre-activation)                             (fc2 dgrad)
+//   EPI_TRANSPOSED fp32 C with bias / fp32 residual / gathered positional rows / C += / split-K atomics;
+//                  32x32 blocks go through a swizzled smem transpose so that every global access is a
+//                  coalesced 4 rows x 128 B                                      (proj, fc2, wgrads, embeds)
+//   EPI_GENERIC    every epilogue field at run time (rare combinations)
+enum { EPI_PLAIN = 0, EPI_GELU = 1, EPI_DACT = 2, EPI_TRANSPOSED = 3, EPI_GENERIC = 4 };
+
+template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <int EPI>
 __global__ void __launch_bounds__(UG_THREADS, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const UmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -138,7 +158,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const uint32_t tfull_bar = bars + 16 * UG_STAGES;     // [2]
   const uint32_t tempty_bar = tfull_bar + 16;           // [2]
   const uint32_t tmem_slot = tempty_bar + 16;           // u32
-  const uint32_t epi_stage = bars + 256;                // [UG_EPI_WARPS] x 4 KB transpose buffers
+  const uint32_t epi_stage = bars + 256;                // [UG_EPI_WARPS] x 4 KB: bias row / transpose buffer
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -160,105 +180,105 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int n_units = p.tiles_m * p.tiles_n * p.split_k;
-  const uint32_t b_box_bytes = (uint32_t)p.block_n * UG_BK * 2;
 
-  if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int tile = u / p.split_k, ks = u % p.split_k;
-        const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
-        const int kb0 = ks * p.kb_per_split;
-        const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-          const uint32_t fb = full_bar + 8 * stage;
-          mbar_expect_tx(fb, UG_A_STAGE_BYTES + b_box_bytes);
-          const uint32_t sa = smem_a + stage * UG_A_STAGE_BYTES;
-          const uint32_t sb = smem_b + stage * UG_B_STAGE_BYTES;
-          if (!p.a_mn_major) {
-            tma_load_2d(sa, &tma_a, fb, kb * UG_BK, m_blk * UG_BM);
-          } else {
-            tma_load_2d(sa, &tma_a, fb, m_blk * UG_BM, kb * UG_BK);
-            tma_load_2d(sa + 8192, &tma_a, fb, m_blk * UG_BM + 64, kb * UG_BK);
+  if (warp < 4) {
+    // warpgroup 0 hands its registers to the epilogue warpgroups (the kernel is compiled for 168)
+    reg_dec<40>();
+    if (warp == 0) {
+      // ================= TMA producer =================
+      if (lane == 0) {
+        const uint32_t b_box_bytes = (uint32_t)p.block_n * UG_BK * 2;
+        uint32_t stage = 0, phase = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+          const int tile = u / p.split_k, ks = u % p.split_k;
+          const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+          const int kb0 = ks * p.kb_per_split;
+          const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+            const uint32_t fb = full_bar + 8 * stage;
+            mbar_expect_tx(fb, UG_A_STAGE_BYTES + b_box_bytes);
+            const uint32_t sa = smem_a + stage * UG_A_STAGE_BYTES;
+            const uint32_t sb = smem_b + stage * UG_B_STAGE_BYTES;
+            if (!p.a_mn_major) {
+              tma_load_2d(sa, &tma_a, fb, kb * UG_BK, m_blk * UG_BM);
+            } else {
+              tma_load_2d(sa, &tma_a, fb, m_blk * UG_BM, kb * UG_BK);
+              tma_load_2d(sa + 8192, &tma_a, fb, m_blk * UG_BM + 64, kb * UG_BK);
+            }
+            if (!p.b_mn_major) {
+              tma_load_2d(sb, &tma_b, fb, kb * UG_BK, n_blk * p.block_n);
+            } else {
+              for (int j = 0; j < p.block_n / 64; ++j)
+                tma_load_2d(sb + j * 8192, &tma_b, fb, n_blk * p.block_n + j * 64, kb * UG_BK);
+            }
+            if (++stage == UG_STAGES) { stage = 0; phase ^= 1; }
           }
-          if (!p.b_mn_major) {
-            tma_load_2d(sb, &tma_b, fb, kb * UG_BK, n_blk * p.block_n);
-          } else {
-            for (int j = 0; j < p.block_n / 64; ++j)
-              tma_load_2d(sb + j * 8192, &tma_b, fb, n_blk * p.block_n + j * 64, kb * UG_BK);
-          }
-          if (++stage == UG_STAGES) { stage = 0; phase ^= 1; }
         }
       }
-    }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn_major << 15) |
-                             ((uint32_t)p.b_mn_major << 16) | ((uint32_t)(p.block_n >> 3) << 17) |
-                             ((uint32_t)(UG_BM >> 4) << 24);
-      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int ks = u % p.split_k;
-        const int kb0 = ks * p.kb_per_split;
-        const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
-        mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * UG_MAX_BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(full_bar + 8 * stage, phase);
+    } else if (warp == 1) {
+      // ================= MMA issuer =================
+      if (lane == 0) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn_major << 15) |
+                               ((uint32_t)p.b_mn_major << 16) | ((uint32_t)(p.block_n >> 3) << 17) |
+                               ((uint32_t)(UG_BM >> 4) << 24);
+        uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+          const int ks = u % p.split_k;
+          const int kb0 = ks * p.kb_per_split;
+          const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+          mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
           tc_fence_after();
-          const uint32_t sa = smem_a + stage * UG_A_STAGE_BYTES;
-          const uint32_t sb = smem_b + stage * UG_B_STAGE_BYTES;
-          const uint64_t adesc0 = p.a_mn_major ? make_desc(sa, p.mn_lbo, p.mn_sbo) : make_desc(sa, 1, 64);
-          const uint64_t bdesc0 = p.b_mn_major ? make_desc(sb, p.mn_lbo, p.mn_sbo) : make_desc(sb, 1, 64);
-          const uint32_t a_adv = p.a_mn_major ? p.mn_kadv : 2u;   // 16-byte units per UMMA_K=16
-          const uint32_t b_adv = p.b_mn_major ? p.mn_kadv : 2u;
+          const uint32_t tmem_d = tmem_base + acc * UG_MAX_BN;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(full_bar + 8 * stage, phase);
+            tc_fence_after();
+            const uint32_t sa = smem_a + stage * UG_A_STAGE_BYTES;
+            const uint32_t sb = smem_b + stage * UG_B_STAGE_BYTES;
+            const uint64_t adesc0 = p.a_mn_major ? make_desc(sa, p.mn_lbo, p.mn_sbo) : make_desc(sa, 1, 64);
+            const uint64_t bdesc0 = p.b_mn_major ? make_desc(sb, p.mn_lbo, p.mn_sbo) : make_desc(sb, 1, 64);
+            const uint32_t a_adv = p.a_mn_major ? p.mn_kadv : 2u;   // 16-byte units per UMMA_K=16
+            const uint32_t b_adv = p.b_mn_major ? p.mn_kadv : 2u;
 #pragma unroll
-          for (int k = 0; k < UG_BK / 16; ++k) {
-            tc_mma_bf16(tmem_d, adesc0 + (uint64_t)(k * a_adv), bdesc0 + (uint64_t)(k * b_adv), idesc,
-                        (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < UG_BK / 16; ++k) {
+              tc_mma_bf16(tmem_d, adesc0 + (uint64_t)(k * a_adv), bdesc0 + (uint64_t)(k * b_adv), idesc,
+                          (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            tc_commit(empty_bar + 8 * stage);          // frees the smem stage when these MMAs retire
+            if (++stage == UG_STAGES) { stage = 0; phase ^= 1; }
           }
-          tc_commit(empty_bar + 8 * stage);          // frees the smem stage when these MMAs retire
-          if (++stage == UG_STAGES) { stage = 0; phase ^= 1; }
+          tc_commit(tfull_bar + 8 * acc);              // accumulator complete -> epilogue
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        tc_commit(tfull_bar + 8 * acc);              // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
-    // ================= epilogue warps =================
-    // 8 warps: two per TMEM lane quarter, each taking half of the tile's columns, 32 columns at a
-    // time.  tcgen05.ld hands every thread ONE ROW (32 consecutive columns); storing that straight to
-    // global memory would touch 32 different cache lines per instruction, so each 32x32 block is
-    // transposed through a private 4 KB swizzled shared-memory buffer first: afterwards a warp
-    // instruction covers 4 rows x 128 contiguous bytes and every global access of the fused
-    // epilogue (bias, residual, positional rows, GELU aux, C) is fully coalesced.
+    // ================= epilogue warpgroups (8 warps, 232 registers each) =================
+    // Two warps per TMEM lane quarter, each taking half of the tile's columns, 32 columns at a time.
+    reg_inc<232>();
     const int q = warp & 3;                          // TMEM lane quarter this warp may touch
-    const int ew = warp - 2;
+    const int ew = warp - 4;
     const int half = ew >> 2;
-    const int c_lo = half * (p.block_n / 2), c_hi = c_lo + p.block_n / 2;
+    const int cols_half = p.block_n / 2;
+    const int c_lo = half * cols_half, c_hi = c_lo + cols_half;
     const uint32_t stg = epi_stage + ew * UG_EPI_STAGE_BYTES;
-    const int sub = lane >> 3, c4 = lane & 7;        // coalesced phase: row i*4+sub, float4 column c4
+    const int sub = lane >> 3, c4 = lane & 7;        // transposed phase: row i*4+sub, float4 column c4
     const avj_epilogue& ep = p.ep;
     // Everything the epilogue ADDS comes from HBM (fp32 residual stream, previous C of a `C +=`, the saved
-    // pre-activation of GELU').  Those loads would each pay a full DRAM round trip in the middle of the
-    // epilogue, so the rows of the NEXT tile are pulled into L2 with bulk prefetches while this tile's
-    // MMAs are still running.
-    const bool want_pf = (ep.residual != nullptr) || (ep.dact_aux != nullptr) || (ep.accumulate && p.split_k == 1);
+    // pre-activation of GELU').  The rows of the NEXT tile are pulled into L2 with bulk prefetches while
+    // this tile's MMAs are still running, so those loads do not pay a DRAM round trip mid-epilogue.
+    const bool want_pf = (EPI == EPI_DACT) || ((EPI == EPI_TRANSPOSED || EPI == EPI_GENERIC) &&
+                         ((ep.residual != nullptr) || (ep.dact_aux != nullptr) || (ep.accumulate && p.split_k == 1)));
     auto prefetch_tile = [&](int u) {
       const int tile = u / p.split_k;
       const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
       const int r = m_blk * UG_BM + q * 32 + lane;
       if (r >= p.M) return;
       const int n0 = n_blk * p.block_n + c_lo;
-      const uint32_t cols = (uint32_t)(p.block_n / 2);
       const int64_t off = map_row(ep.out_map, r) * (int64_t)p.ldc + n0;
-      if (ep.residual) l2_prefetch(ep.residual + off, cols * 4);
-      if (ep.accumulate && p.split_k == 1) l2_prefetch(reinterpret_cast<const float*>(p.C) + off, cols * 4);
-      if (ep.dact_aux) l2_prefetch(reinterpret_cast<const bf16*>(ep.dact_aux) + (int64_t)r * p.N + n0, cols * 2);
+      if (ep.residual) l2_prefetch(ep.residual + off, cols_half * 4);
+      if (ep.accumulate && p.split_k == 1) l2_prefetch(reinterpret_cast<const float*>(p.C) + off, cols_half * 4);
+      if (ep.dact_aux) l2_prefetch(reinterpret_cast<const bf16*>(ep.dact_aux) + (int64_t)r * p.N + n0, cols_half * 2);
     };
     if (want_pf && (int)blockIdx.x < n_units) prefetch_tile(blockIdx.x);
     uint32_t acc = 0, acc_phase = 0;
@@ -267,14 +287,91 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
       const int row_base = m_blk * UG_BM + q * 32;
       if (want_pf && u + (int)gridDim.x < n_units) prefetch_tile(u + gridDim.x);
-      mbar_wait(tfull_bar + 8 * acc, acc_phase);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * UG_MAX_BN;
       uint32_t raw[32];
-      tmem_ld32_issue(taddr + c_lo, raw);
 
-      if (!p.epi_transposed) {
+      if (EPI == EPI_PLAIN || EPI == EPI_GELU || EPI == EPI_DACT) {
         // ---------------- direct: thread == row, 32 consecutive columns per step ----------------
+        // the warp's bias segment goes to shared memory once per tile (broadcast reads afterwards)
+        const bool has_bias = (EPI != EPI_DACT) && ep.bias != nullptr;
+        if (has_bias) {
+          __syncwarp();                               // every lane is done with the previous tile's bias
+          if (lane * 4 < cols_half) sts_f4(stg + lane * 16, ld_f4(ep.bias + n_blk * p.block_n + c_lo + lane * 4));
+          __syncwarp();
+        }
+        const int64_t row = row_base + lane;
+        const bool row_ok = row < p.M;
+        const int64_t prow = row_ok ? map_row(ep.out_map, row) : 0;
+        mbar_wait(tfull_bar + 8 * acc, acc_phase);
+        tc_fence_after();
+        tmem_ld32_issue(taddr + c_lo, raw);
+        for (int c = c_lo; c < c_hi; c += 32) {
+          const int n0 = n_blk * p.block_n + c;
+          uint4 aux[4];
+          if (EPI == EPI_DACT) {
+            const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.dact_aux) + row * (int64_t)p.N + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) aux[j] = row_ok ? ap[j] : make_uint4(0u, 0u, 0u, 0u);
+          }
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+          if (c + 32 < c_hi) {
+            tmem_ld32_issue(taddr + c + 32, raw);
+          } else {
+            tc_fence_before();
+            mbar_arrive(tempty_bar + 8 * acc);
+          }
+          if (has_bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = lds_f4(stg + (c - c_lo + j * 4) * 4);
+              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
+          }
+          if (!row_ok) continue;
+          if (EPI == EPI_GELU) {
+            if (ep.pre_out) {
+              uint4* pp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.pre_out) + row * (int64_t)p.N + n0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                pp[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                   pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_fwd<true>(v[i]);
+          }
+          if (EPI == EPI_DACT) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t w[4] = {aux[j].x, aux[j].y, aux[j].z, aux[j].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float x0, x1;
+                unpack_bf16x2(w[e], x0, x1);
+                v[8 * j + 2 * e] *= gelu_bwd<true>(x0);
+                v[8 * j + 2 * e + 1] *= gelu_bwd<true>(x1);
+              }
+            }
+          }
+          if (ep.out_dtype == AVJ_F32) {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + prow * (int64_t)p.ldc + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.C) + prow * (int64_t)p.ldc + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              op[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                 pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+          }
+        }
+      } else if (EPI == EPI_GENERIC) {
+        // ---------------- generic direct path: every epilogue field evaluated at run time ----------------
+        mbar_wait(tfull_bar + 8 * acc, acc_phase);
+        tc_fence_after();
+        tmem_ld32_issue(taddr + c_lo, raw);
         const int64_t row = row_base + lane;
         const bool row_ok = row < p.M;
         for (int c = c_lo; c < c_hi; c += 32) {
@@ -297,103 +394,74 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
               for (int i = 0; i < 32; i += 4) atomicAdd(reinterpret_cast<float4*>(out + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
             } else {
-              epilogue_apply_store<TAct, 32, true>(ep, p.C, p.ldc, p.N, row, n0, v, add);
+              epilogue_apply_store<bf16, 32, true>(ep, p.C, p.ldc, p.N, row, n0, v, add);
             }
           }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        continue;
-      }
-
-      // ---------------- transposed: coalesced 4 rows x 128 B per warp instruction ----------------
-      int prow[8];                                   // physical C row of my 8 rows, -1 = past M
+      } else {
+        // ---------------- transposed: coalesced 4 rows x 128 B per warp instruction, fp32 C ----------------
+        int prow[8];                                   // physical C row of my 8 rows, -1 = past M
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = row_base + i * 4 + sub;
-        prow[i] = r < p.M ? (int)map_row(ep.out_map, r) : -1;
-      }
-      for (int c = c_lo; c < c_hi; c += 32) {
-        const int n = n_blk * p.block_n + c + c4 * 4;
-        // ---- addends that do not depend on the accumulator: issue all loads before the TMEM wait
-        float4 add[8];
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.split_k == 1) {
-          if (ep.bias) b4 = ld_f4(ep.bias + n);
+        for (int i = 0; i < 8; ++i) {
+          const int r = row_base + i * 4 + sub;
+          prow[i] = r < p.M ? (int)map_row(ep.out_map, r) : -1;
+        }
+        mbar_wait(tfull_bar + 8 * acc, acc_phase);
+        tc_fence_after();
+        tmem_ld32_issue(taddr + c_lo, raw);
+        for (int c = c_lo; c < c_hi; c += 32) {
+          const int n = n_blk * p.block_n + c + c4 * 4;
+          // ---- addends that do not depend on the accumulator: issue all loads before the TMEM wait
+          float4 add[8];
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.split_k == 1) {
+            if (ep.bias) b4 = ld_f4(ep.bias + n);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              add[i] = b4;
+              if (prow[i] < 0) continue;
+              const int64_t off = (int64_t)prow[i] * p.ldc + n;
+              if (ep.residual) f4_add(add[i], ld_f4(ep.residual + off));
+              if (ep.pos) {
+                const int r = row_base + i * 4 + sub;
+                const int64_t pr = ep.pos_idx ? ep.pos_idx[r] : (int64_t)(r % ep.pos_rows);
+                f4_add(add[i], ld_f4(ep.pos + pr * (int64_t)p.N + n));
+              }
+              if (ep.accumulate) f4_add(add[i], ld_f4(reinterpret_cast<const float*>(p.C) + off));
+            }
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t dst = stg + lane * 128 + ((j ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(raw[4 * j]), "r"(raw[4 * j + 1]),
+                         "r"(raw[4 * j + 2]), "r"(raw[4 * j + 3]) : "memory");
+          }
+          if (c + 32 < c_hi) {
+            tmem_ld32_issue(taddr + c + 32, raw);      // next block is in flight while this one is stored
+          } else {
+            tc_fence_before();
+            mbar_arrive(tempty_bar + 8 * acc);         // accumulator drained: the MMA warp may reuse it
+          }
+          __syncwarp();
+          float4 v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            add[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int rl = i * 4 + sub;
+            v[i] = lds_f4(stg + rl * 128 + ((c4 ^ (rl & 7)) << 4));
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
             if (prow[i] < 0) continue;
-            const int64_t off = (int64_t)prow[i] * p.ldc + n;
-            if (ep.residual) add[i] = ld_f4(ep.residual + off);
-            if (ep.pos) {
-              const int r = row_base + i * 4 + sub;
-              const int64_t pr = ep.pos_idx ? ep.pos_idx[r] : (int64_t)(r % ep.pos_rows);
-              f4_add(add[i], ld_f4(ep.pos + pr * (int64_t)p.N + n));
+            float* out = reinterpret_cast<float*>(p.C) + (int64_t)prow[i] * p.ldc + n;
+            if (p.split_k > 1) {
+              atomicAdd(reinterpret_cast<float4*>(out), v[i]);
+            } else {
+              f4_add(v[i], add[i]);
+              *reinterpret_cast<float4*>(out) = v[i];
             }
-            if (ep.accumulate) f4_add(add[i], ld_f4(reinterpret_cast<const float*>(p.C) + off));
           }
-        }
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t dst = stg + lane * 128 + ((j ^ (lane & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(raw[4 * j]), "r"(raw[4 * j + 1]),
-                       "r"(raw[4 * j + 2]), "r"(raw[4 * j + 3]) : "memory");
-        }
-        if (c + 32 < c_hi) {
-          tmem_ld32_issue(taddr + c + 32, raw);      // next block is in flight while this one is stored
-        } else {
-          tc_fence_before();
-          mbar_arrive(tempty_bar + 8 * acc);         // accumulator drained: the MMA warp may reuse it
-        }
-        __syncwarp();
-        float4 v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rl = i * 4 + sub;
-          const uint32_t src = stg + rl * 128 + ((c4 ^ (rl & 7)) << 4);
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(src) : "memory");
-        }
-        __syncwarp();
-        if (p.split_k > 1) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (prow[i] >= 0)
-              atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (int64_t)prow[i] * p.ldc + n), v[i]);
-          continue;
-        }
-        uint2 aux[8];
-        if (ep.dact_aux) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            aux[i] = make_uint2(0u, 0u);
-            if (prow[i] >= 0)
-              aux[i] = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(ep.dact_aux) +
-                                                       (int64_t)(row_base + i * 4 + sub) * p.N + n);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (prow[i] < 0) continue;
-          float4 a = v[i];
-          f4_add(a, b4);
-          if (ep.act == 1) {
-            if (ep.pre_out)
-              *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.pre_out) + (int64_t)(row_base + i * 4 + sub) * p.N + n) =
-                  make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
-            a.x = gelu_fwd<true>(a.x); a.y = gelu_fwd<true>(a.y); a.z = gelu_fwd<true>(a.z); a.w = gelu_fwd<true>(a.w);
-          }
-          if (ep.dact_aux) {
-            float x0, x1, x2, x3;
-            unpack_bf16x2(aux[i].x, x0, x1); unpack_bf16x2(aux[i].y, x2, x3);
-            a.x *= gelu_bwd<true>(x0); a.y *= gelu_bwd<true>(x1); a.z *= gelu_bwd<true>(x2); a.w *= gelu_bwd<true>(x3);
-          }
-          f4_add(a, add[i]);
-          const int64_t off = (int64_t)prow[i] * p.ldc + n;
-          if (ep.out_dtype == AVJ_F32)
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + off) = a;
-          else
-            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.C) + off) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -529,11 +597,6 @@ int avj_gemm_umma(int layout, const void* A, const void* B, void* C, int M, int 
   p.kb_per_split = (p.k_blocks + p.split_k - 1) / p.split_k;
   p.split_k = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;   // drop empty splits
 
-  // fp32 outputs (residual stream, weight gradients) take the smem-transposed coalesced epilogue; bf16
-  // outputs write 64 contiguous bytes per thread already and skip the extra shared-memory round trip.
-  static const uint32_t epi_mode = env_u32("AVJ_EPI_MODE", 0);      // 0 auto, 1 direct, 2 transposed
-  p.epi_transposed = epi_mode == 0 ? (ep.out_dtype == AVJ_F32) : (epi_mode == 2);
-
   CUtensorMap ma, mb;
   int rc;
   if (!p.a_mn_major) rc = get_tensor_map(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, UG_BK, UG_BM, &ma);
@@ -543,16 +606,31 @@ int avj_gemm_umma(int layout, const void* A, const void* B, void* C, int M, int 
   else               rc = get_tensor_map(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, UG_BK, &mb);
   if (rc) return rc;
 
+  // ---- epilogue specialisation
+  const bool adds = ep.residual || ep.pos || ep.accumulate;
+  int epi;
+  static const uint32_t force_generic = env_u32("AVJ_EPI_GENERIC", 0);
+  if (force_generic) epi = EPI_GENERIC;
+  else if (ep.out_dtype == AVJ_F32) epi = (ep.act || ep.dact_aux) ? EPI_GENERIC : EPI_TRANSPOSED;
+  else if (adds || p.split_k > 1 || (ep.act && ep.dact_aux)) epi = EPI_GENERIC;
+  else if (ep.act) epi = EPI_GELU;
+  else if (ep.dact_aux) epi = EPI_DACT;
+  else epi = EPI_PLAIN;
+
+  typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const UmmaParams);
+  static const kern_t kerns[5] = {gemm_umma_kernel<EPI_PLAIN>, gemm_umma_kernel<EPI_GELU>, gemm_umma_kernel<EPI_DACT>,
+                                  gemm_umma_kernel<EPI_TRANSPOSED>, gemm_umma_kernel<EPI_GENERIC>};
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_umma_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, UG_SMEM_BYTES);
+    for (int i = 0; i < 5 && attr_err == cudaSuccess; ++i)
+      attr_err = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, UG_SMEM_BYTES);
   });
   AVJ_CHECK(attr_err == cudaSuccess, "cudaFuncSetAttribute(gemm_umma_kernel) failed: %s", cudaGetErrorString(attr_err));
 
   const int units = tiles * p.split_k;
   const int grid = units < sms ? units : sms;
-  gemm_umma_kernel<bf16><<<grid, UG_THREADS, UG_SMEM_BYTES, s>>>(ma, mb, p);
+  kerns[epi]<<<grid, UG_THREADS, UG_SMEM_BYTES, s>>>(ma, mb, p);
   AVJ_LAUNCH_CHECK();
   return 0;
 }

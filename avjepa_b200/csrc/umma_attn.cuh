@@ -75,10 +75,10 @@ __device__ __forceinline__ void ua_st32(uint32_t taddr, const float* v) {
 // 16-byte chunk c of row r lands at r*128 + ((c ^ (r & 7)) << 4).
 template <int HDP, int ROWS = 128>
 __device__ __forceinline__ void ua_stage(uint32_t tile, const bf16* __restrict__ src, int64_t row_stride, int row0,
-                                         int nrows_total, int hd, int lane) {
+                                         int nrows_total, int hd, int tid, int nthreads = 32) {
   constexpr int CH = HDP / 8;
   const int hd_ch = hd / 8;
-  for (int e = lane; e < ROWS * CH; e += 32) {
+  for (int e = tid; e < ROWS * CH; e += nthreads) {
     const int r = e / CH, c = e % CH;
     const uint32_t dst = tile + r * 128 + ((c ^ (r & 7)) << 4);
     if (row0 + r < nrows_total && c < hd_ch) {
@@ -88,6 +88,10 @@ __device__ __forceinline__ void ua_stage(uint32_t tile, const bf16* __restrict__
     }
   }
 }
+
+// Register re-partitioning between warpgroups (warps 4k..4k+3 must all execute the same one).
+template <int R> __device__ __forceinline__ void ua_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ __forceinline__ void ua_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
 
 __device__ __forceinline__ float ua_exp2(float x) {
   float y;

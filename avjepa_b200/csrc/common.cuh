@@ -120,29 +120,39 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 }
 
 // Production-mode GELU (results are rounded to bf16 anyway; fp32 check mode keeps erff()):
-//   Phi(x) ~= sigmoid(x * (c0 + c1 x^2 + c2 x^4)),  x^2 clamped to 50
+//   Phi(x) ~= sigmoid(u),   u = x (c0 + c1 x^2 + c2 x^4),  x^2 clamped to 50
 // fitted to the exact normal CDF: |x Phi - gelu_erf(x)| <= 2.6e-5 and |d/dx - gelu_erf'(x)| <= 1.1e-4 for
-// all x (bf16 has a relative step of 3.9e-3).  9 FMA-pipe/MUFU instructions per element forward, 13
-// backward -- the GEMM epilogue that applies it is instruction-issue bound, so this matters.
-__device__ __forceinline__ void gelu_fast_parts(float x, float& cdf, float& dcdf_x) {
-  const float c0 = 1.5950157685561237f, c1 = 0.07401129205320253f, c2 = -0.0007030335786691012f;
+// all x with an exact sigmoid (bf16 has a relative step of 3.9e-3).
+//   forward : sigmoid(u) = 0.5 + 0.5 tanh(u/2) with tanh.approx.f32 (ONE MUFU op, <= 2^-11 relative):
+//             8 instructions per element -- the fc1 epilogue that applies it is MUFU/issue bound.
+//   backward: s = 1/(1+e), e = exp(-u); s(1-s) = e s^2 has no cancellation near saturation (tanh.approx
+//             would turn its 2^-11 error into a 1e-2 error of GELU' for x > 3.5), 13 instructions.
+#define AVJ_GELU_C0 1.5950157685561237f
+#define AVJ_GELU_C1 0.07401129205320253f
+#define AVJ_GELU_C2 -0.0007030335786691012f
+__device__ __forceinline__ float gelu_fast_fwd(float x) {
   const float x2 = fminf(x * x, 50.0f);
-  const float p = fmaf(fmaf(c2, x2, c1), x2, c0);
-  const float u = x * p;
+  const float h = x * fmaf(fmaf(0.5f * AVJ_GELU_C2, x2, 0.5f * AVJ_GELU_C1), x2, 0.5f * AVJ_GELU_C0);   // u / 2
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return x * fmaf(0.5f, t, 0.5f);
+}
+__device__ __forceinline__ float gelu_fast_bwd(float x) {
+  const float x2 = fminf(x * x, 50.0f);
+  const float u = x * fmaf(fmaf(AVJ_GELU_C2, x2, AVJ_GELU_C1), x2, AVJ_GELU_C0);
   float e, s;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u * -1.4426950408889634f));
+  e = fminf(e, 1e30f);                                   // keep e * s * s finite for very negative x
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(1.0f + e));
-  cdf = s;
-  // x * d(cdf)/dx = x * s (1 - s) * (c0 + 3 c1 x^2 + 5 c2 x^4)
-  const float du = fmaf(fmaf(5.0f * c2, x2, 3.0f * c1), x2, c0);
-  dcdf_x = x * fmaf(-s, s, s) * du;
+  const float du = fmaf(fmaf(5.0f * AVJ_GELU_C2, x2, 3.0f * AVJ_GELU_C1), x2, AVJ_GELU_C0);
+  return fmaf(x * (e * s * s), du, s);                   // Phi + x Phi'
 }
 template <bool FAST> __device__ __forceinline__ float gelu_fwd(float x) {
-  if (FAST) { float c, d; gelu_fast_parts(x, c, d); return x * c; }
+  if (FAST) return gelu_fast_fwd(x);
   return gelu_erf(x);
 }
 template <bool FAST> __device__ __forceinline__ float gelu_bwd(float x) {
-  if (FAST) { float c, d; gelu_fast_parts(x, c, d); return c + d; }
+  if (FAST) return gelu_fast_bwd(x);
   return gelu_erf_grad(x);
 }
 

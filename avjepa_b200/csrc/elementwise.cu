@@ -215,24 +215,35 @@ extern "C" int avj_fill_mask_tokens(const float* mask_token, const float* pos, c
 // reduction).  Slab = 128 rows; one CTA handles a slab x 256 columns (8 cols per thread x 32
 // threads x 8 row-lanes).
 // ------------------------------------------------------------------------------------------
-#define COLSUM_SLAB 256
+#define COLSUM_MAX_Y 64
 
 extern "C" int64_t avj_colsum_ws_floats(int rows, int D) {
-  int64_t slabs = (rows + COLSUM_SLAB - 1) / COLSUM_SLAB;
-  return slabs * (int64_t)D;
+  (void)rows;
+  return (int64_t)COLSUM_MAX_Y * D;
 }
 
+// grid (ceil(D/256), Y): block (32, 8) owns 256 columns x one row range; 4 independent 16-byte loads per
+// thread are kept in flight.  Deterministic two-stage reduction (no atomics): partials -> ws[Y][D].
 template <typename T>
-__global__ void colsum_partial_kernel(const T* __restrict__ in, int ld, avj_rowmap map, float* __restrict__ ws,
-                                      int rows, int D) {
-  // blockDim = (32, 8): x -> 8-col group, y -> row lane
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const T* __restrict__ in, int ld, avj_rowmap map, float* __restrict__ ws,
+                      int rows, int D, int chunk) {
   __shared__ float sm[8][32][8 + 1];
   const int c0 = (blockIdx.x * 32 + threadIdx.x) * 8;
-  const int slab = blockIdx.y;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (c0 < D) {
-    const int r_end = min(rows, (slab + 1) * COLSUM_SLAB);
-    for (int r = slab * COLSUM_SLAB + threadIdx.y; r < r_end; r += 8) {
+    const int r_beg = blockIdx.y * chunk, r_end = min(rows, r_beg + chunk);
+    int r = r_beg + threadIdx.y;
+    for (; r + 24 < r_end; r += 32) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load8<T>(in + map_row(map, r + 8 * u) * ld + c0, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[u][j];
+    }
+    for (; r < r_end; r += 8) {
       float v[8];
       load8<T>(in + map_row(map, r) * ld + c0, v);
 #pragma unroll
@@ -248,16 +259,17 @@ __global__ void colsum_partial_kernel(const T* __restrict__ in, int ld, avj_rowm
       float s = 0.f;
 #pragma unroll
       for (int y = 0; y < 8; ++y) s += sm[y][threadIdx.x][j];
-      ws[(int64_t)slab * D + c0 + j] = s;
+      ws[(int64_t)blockIdx.y * D + c0 + j] = s;
     }
   }
 }
 
-__global__ void colsum_final_kernel(const float* __restrict__ ws, float* __restrict__ out, int slabs, int D) {
+__global__ void colsum_final_kernel(const float* __restrict__ ws, float* __restrict__ out, int ny, int D) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= D) return;
   float s = 0.f;
-  for (int i = 0; i < slabs; ++i) s += ws[(int64_t)i * D + c];
+#pragma unroll 8
+  for (int i = 0; i < ny; ++i) s += ws[(int64_t)i * D + c];
   out[c] += s;
 }
 
@@ -266,14 +278,21 @@ extern "C" int avj_colsum(const void* in, int in_dtype, int ld, avj_rowmap map, 
   AVJ_CHECK(D % 8 == 0 && ld % 8 == 0, "avj_colsum: D/ld must be multiples of 8");
   if (rows == 0 || D == 0) return 0;
   AvjProfScope prof(AVJ_FAM_COLSUM, (double)rows * D * (in_dtype == AVJ_BF16 ? 2 : 4), stream);
-  const int slabs = (rows + COLSUM_SLAB - 1) / COLSUM_SLAB;
-  dim3 grid((D + 255) / 256, slabs), block(32, 8);
+  const int gx = (D + 255) / 256;
+  int ny = (4 * avj_num_sms() + gx - 1) / gx;                 // ~4 CTAs per SM
+  if (ny > COLSUM_MAX_Y) ny = COLSUM_MAX_Y;
+  if (ny > (rows + 63) / 64) ny = (rows + 63) / 64;           // at least 64 rows per CTA
+  if (ny < 1) ny = 1;
+  int chunk = (rows + ny - 1) / ny;
+  chunk = (chunk + 7) / 8 * 8;
+  ny = (rows + chunk - 1) / chunk;
+  dim3 grid(gx, ny), block(32, 8);
   if (in_dtype == AVJ_BF16)
-    colsum_partial_kernel<bf16><<<grid, block, 0, as_stream(stream)>>>((const bf16*)in, ld, map, ws, rows, D);
+    colsum_partial_kernel<bf16><<<grid, block, 0, as_stream(stream)>>>((const bf16*)in, ld, map, ws, rows, D, chunk);
   else
-    colsum_partial_kernel<float><<<grid, block, 0, as_stream(stream)>>>((const float*)in, ld, map, ws, rows, D);
+    colsum_partial_kernel<float><<<grid, block, 0, as_stream(stream)>>>((const float*)in, ld, map, ws, rows, D, chunk);
   AVJ_LAUNCH_CHECK();
-  colsum_final_kernel<<<(D + 127) / 128, 128, 0, as_stream(stream)>>>(ws, out, slabs, D);
+  colsum_final_kernel<<<(D + 63) / 64, 64, 0, as_stream(stream)>>>(ws, out, ny, D);
   AVJ_LAUNCH_CHECK();
   return 0;
 }

@@ -40,6 +40,7 @@ struct UmmaParams {
   int split_k;           // >= 1
   int kb_per_split;
   int a_mn_major, b_mn_major;
+  int l2_prefetch;       // bulk-prefetch next tile's epilogue operands into L2
   uint32_t mn_lbo, mn_sbo, mn_kadv;   // MN-major descriptor fields / k-advance (16 B units)
   void* C;
   avj_epilogue ep;
@@ -267,8 +268,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // Everything the epilogue ADDS comes from HBM (fp32 residual stream, previous C of a `C +=`, the saved
     // pre-activation of GELU').  The rows of the NEXT tile are pulled into L2 with bulk prefetches while
     // this tile's MMAs are still running, so those loads do not pay a DRAM round trip mid-epilogue.
-    const bool want_pf = (EPI == EPI_DACT) || ((EPI == EPI_TRANSPOSED || EPI == EPI_GENERIC) &&
-                         ((ep.residual != nullptr) || (ep.dact_aux != nullptr) || (ep.accumulate && p.split_k == 1)));
+    const bool want_pf = p.l2_prefetch && ((EPI == EPI_DACT) || ((EPI == EPI_TRANSPOSED || EPI == EPI_GENERIC) &&
+                         ((ep.residual != nullptr) || (ep.dact_aux != nullptr) || (ep.accumulate && p.split_k == 1))));
     auto prefetch_tile = [&](int u) {
       const int tile = u / p.split_k;
       const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
@@ -411,23 +412,33 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         tmem_ld32_issue(taddr + c_lo, raw);
         for (int c = c_lo; c < c_hi; c += 32) {
           const int n = n_blk * p.block_n + c + c4 * 4;
-          // ---- addends that do not depend on the accumulator: issue all loads before the TMEM wait
-          float4 add[8];
+          // ---- addends that do not depend on the accumulator: ALL loads are issued back to back (rows past
+          // M are clamped to a valid row and discarded) so one chunk costs one memory round trip, and they
+          // are in flight while the TMEM load completes
+          float4 add[8], add2[8];
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          const bool two = ep.accumulate && (ep.residual || ep.pos);
           if (p.split_k == 1) {
             if (ep.bias) b4 = ld_f4(ep.bias + n);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              add[i] = b4;
-              if (prow[i] < 0) continue;
-              const int64_t off = (int64_t)prow[i] * p.ldc + n;
-              if (ep.residual) f4_add(add[i], ld_f4(ep.residual + off));
-              if (ep.pos) {
-                const int r = row_base + i * 4 + sub;
+            for (int i = 0; i < 8; ++i) { add[i] = make_float4(0.f, 0.f, 0.f, 0.f); add2[i] = add[i]; }
+            if (ep.residual) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) add[i] = ld_f4(ep.residual + (int64_t)max(prow[i], 0) * p.ldc + n);
+            } else if (ep.pos) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int r = min(row_base + i * 4 + sub, p.M - 1);
                 const int64_t pr = ep.pos_idx ? ep.pos_idx[r] : (int64_t)(r % ep.pos_rows);
-                f4_add(add[i], ld_f4(ep.pos + pr * (int64_t)p.N + n));
+                add[i] = ld_f4(ep.pos + pr * (int64_t)p.N + n);
               }
-              if (ep.accumulate) f4_add(add[i], ld_f4(reinterpret_cast<const float*>(p.C) + off));
+            }
+            if (ep.accumulate) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 t = ld_f4(reinterpret_cast<const float*>(p.C) + (int64_t)max(prow[i], 0) * p.ldc + n);
+                if (two) add2[i] = t; else add[i] = t;
+              }
             }
           }
           tmem_ld_wait();
@@ -458,7 +469,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             if (p.split_k > 1) {
               atomicAdd(reinterpret_cast<float4*>(out), v[i]);
             } else {
+              f4_add(v[i], b4);
               f4_add(v[i], add[i]);
+              if (two) f4_add(v[i], add2[i]);
               *reinterpret_cast<float4*>(out) = v[i];
             }
           }
@@ -606,6 +619,8 @@ int avj_gemm_umma(int layout, const void* A, const void* B, void* C, int M, int 
   else               rc = get_tensor_map(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, UG_BK, &mb);
   if (rc) return rc;
 
+  static const uint32_t l2pf = env_u32("AVJ_GEMM_L2PF", 1);
+  p.l2_prefetch = (int)l2pf;
   // ---- epilogue specialisation
   const bool adds = ep.residual || ep.pos || ep.accumulate;
   int epi;

@@ -112,8 +112,13 @@ __device__ __forceinline__ float4 load4_as_f32<bf16>(const bf16* p, int c) {
   return f;
 }
 
+// One warp per row, rows strided over the grid.  Registers hold only the row being processed (x, dy, and
+// the residual gradient, all requested up front so a row costs ONE memory round trip); the per-column
+// d(gamma)/d(beta) partial sums live in a warp-private shared-memory slab (each lane owns its columns,
+// so no synchronisation is needed until the final cross-warp reduction).  That keeps the kernel at
+// <= 96 registers, i.e. 2-3 blocks (16-24 warps) per SM instead of one.
 template <typename TDY, typename TLP, int NV4>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+__global__ void __launch_bounds__(LN_WARPS * 32, 2)
 layernorm_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
                      float* __restrict__ dx, TLP* __restrict__ dx_lp, float* __restrict__ ws, int want_dgamma,
@@ -121,31 +126,49 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ x, co
   extern __shared__ float sm[];   // [LN_WARPS][2][D] partials, only when want_dgamma
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = D / 4;
-  float4 ag[NV4], ab[NV4];
+  float4* sg = reinterpret_cast<float4*>(sm + (size_t)warp * 2 * D);
+  float4* sb = sg + nvec;
+  if (want_dgamma) {
 #pragma unroll
-  for (int i = 0; i < NV4; ++i) { ag[i] = make_float4(0.f, 0.f, 0.f, 0.f); ab[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    for (int i = 0; i < NV4; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) { sg[c] = make_float4(0.f, 0.f, 0.f, 0.f); sb[c] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    }
+  }
 
   for (int64_t r = (int64_t)blockIdx.x * LN_WARPS + warp; r < rows; r += (int64_t)gridDim.x * LN_WARPS) {
-    const float mu = mean[r], rs = rstd[r];
     const float4* xr = reinterpret_cast<const float4*>(x + r * D);
     const TDY* dyr = dy + r * D;
-    float4 xh[NV4], g[NV4];
+    float4 xv[NV4], d[NV4], dr[NV4];
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        xv[i] = xr[c];
+        d[i] = load4_as_f32<TDY>(dyr, c);
+        dr[i] = dres ? reinterpret_cast<const float4*>(dres + r * D)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        xv[i] = make_float4(0.f, 0.f, 0.f, 0.f); d[i] = xv[i]; dr[i] = xv[i];
+      }
+    }
+    const float mu = mean[r], rs = rstd[r];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV4; ++i) {
       const int c = lane + i * 32;
       if (c < nvec) {
-        const float4 xv = xr[c];
-        const float4 d = load4_as_f32<TDY>(dyr, c);
         const float4 gm = gamma ? reinterpret_cast<const float4*>(gamma)[c] : make_float4(1.f, 1.f, 1.f, 1.f);
-        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        g[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
-        s1 += g[i].x + g[i].y + g[i].z + g[i].w;
-        s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
-        ag[i].x += d.x * xh[i].x; ag[i].y += d.y * xh[i].y; ag[i].z += d.z * xh[i].z; ag[i].w += d.w * xh[i].w;
-        ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
-      } else {
-        xh[i] = make_float4(0.f, 0.f, 0.f, 0.f); g[i] = xh[i];
+        // xv <- normalised x, d stays dy, g = dy * gamma folded into the sums
+        xv[i] = make_float4((xv[i].x - mu) * rs, (xv[i].y - mu) * rs, (xv[i].z - mu) * rs, (xv[i].w - mu) * rs);
+        if (want_dgamma) {
+          float4 a = sg[c], bb = sb[c];
+          a.x += d[i].x * xv[i].x; a.y += d[i].y * xv[i].y; a.z += d[i].z * xv[i].z; a.w += d[i].w * xv[i].w;
+          bb.x += d[i].x; bb.y += d[i].y; bb.z += d[i].z; bb.w += d[i].w;
+          sg[c] = a; sb[c] = bb;
+        }
+        d[i] = make_float4(d[i].x * gm.x, d[i].y * gm.y, d[i].z * gm.z, d[i].w * gm.w);
+        s1 += d[i].x + d[i].y + d[i].z + d[i].w;
+        s2 += d[i].x * xv[i].x + d[i].y * xv[i].y + d[i].z * xv[i].z + d[i].w * xv[i].w;
       }
     }
     const float m1 = warp_sum(s1) / (float)D;
@@ -154,12 +177,8 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ x, co
     for (int i = 0; i < NV4; ++i) {
       const int c = lane + i * 32;
       if (c < nvec) {
-        float4 o = make_float4(rs * (g[i].x - m1 - xh[i].x * m2), rs * (g[i].y - m1 - xh[i].y * m2),
-                               rs * (g[i].z - m1 - xh[i].z * m2), rs * (g[i].w - m1 - xh[i].w * m2));
-        if (dres) {
-          const float4 dr = reinterpret_cast<const float4*>(dres + r * D)[c];
-          o.x += dr.x; o.y += dr.y; o.z += dr.z; o.w += dr.w;
-        }
+        const float4 o = make_float4(dr[i].x + rs * (d[i].x - m1 - xv[i].x * m2), dr[i].y + rs * (d[i].y - m1 - xv[i].y * m2),
+                                     dr[i].z + rs * (d[i].z - m1 - xv[i].z * m2), dr[i].w + rs * (d[i].w - m1 - xv[i].w * m2));
         reinterpret_cast<float4*>(dx + r * D)[c] = o;
         if (dx_lp) {
           if (sizeof(TLP) == 4) {
@@ -174,16 +193,6 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ x, co
   }
 
   if (want_dgamma) {
-    float* sg = sm + (size_t)warp * 2 * D;
-    float* sb = sg + D;
-#pragma unroll
-    for (int i = 0; i < NV4; ++i) {
-      const int c = lane + i * 32;
-      if (c < nvec) {
-        reinterpret_cast<float4*>(sg)[c] = ag[i];
-        reinterpret_cast<float4*>(sb)[c] = ab[i];
-      }
-    }
     __syncthreads();
     for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
       float t = 0.f;
@@ -194,14 +203,25 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ x, co
   }
 }
 
-__global__ void layernorm_bwd_final_kernel(const float* __restrict__ ws, int nblocks, int D,
-                                           float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * D) return;
+// cross-block reduction of the [nblocks][2D] partials: 32 columns x 8 row groups per block
+__global__ void __launch_bounds__(256)
+layernorm_bwd_final_kernel(const float* __restrict__ ws, int nblocks, int D,
+                           float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
   float t = 0.f;
-  for (int b = 0; b < nblocks; ++b) t += ws[(size_t)b * 2 * D + c];
-  if (c < D) { if (dgamma) dgamma[c] += t; }
-  else { if (dbeta) dbeta[c - D] += t; }
+  if (c < 2 * D)
+    for (int b = ty; b < nblocks; b += 8) t += ws[(size_t)b * 2 * D + c];
+  red[ty][tx] = t;
+  __syncthreads();
+  if (ty == 0 && c < 2 * D) {
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v += red[j][tx];
+    if (c < D) { if (dgamma) dgamma[c] += v; }
+    else { if (dbeta) dbeta[c - D] += v; }
+  }
 }
 
 template <typename TDY, typename TLP>
@@ -217,6 +237,7 @@ static int launch_ln_bwd(const TDY* dy, const float* x, const float* gamma, cons
   case NV: {                                                                                                  \
     auto k = layernorm_bwd_kernel<TDY, TLP, NV>;                                                              \
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);    \
     k<<<grid, LN_WARPS * 32, smem, s>>>(dy, x, gamma, mean, rstd, dres, dx, dx_lp, ws, want, rows, D);          \
   } break;
   switch (nv4) {
@@ -227,7 +248,7 @@ static int launch_ln_bwd(const TDY* dy, const float* x, const float* gamma, cons
 #undef LNB_CASE
   AVJ_LAUNCH_CHECK();
   if (want) {
-    layernorm_bwd_final_kernel<<<(2 * D + 127) / 128, 128, 0, s>>>(ws, grid, D, dgamma, dbeta);
+    layernorm_bwd_final_kernel<<<(2 * D + 31) / 32, 256, 0, s>>>(ws, grid, D, dgamma, dbeta);
     AVJ_LAUNCH_CHECK();
   }
   return 0;

@@ -31,10 +31,25 @@ __device__ __forceinline__ void ua_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
-__device__ __forceinline__ uint64_t ua_desc(uint32_t saddr, uint32_t lbo16, uint32_t sbo16) {
+// shared-memory matrix descriptor (sm_100 version field = 1); layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+__device__ __forceinline__ uint64_t ua_desc(uint32_t saddr, uint32_t lbo16, uint32_t sbo16, uint32_t layout = 2) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(lbo16 & 0x3FFF) << 16) | ((uint64_t)(sbo16 & 0x3FFF) << 32) |
-         (1ull << 46) | (2ull << 61);
+         (1ull << 46) | ((uint64_t)layout << 61);
 }
+
+// Geometry of an operand tile whose rows hold HDP bf16 of one head: HDP = 64 -> 128-byte rows, SWIZZLE_128B;
+// HDP = 32 -> 64-byte rows, SWIZZLE_64B (half the shared memory and L2 traffic of padding to 128 bytes).
+template <int HDP> struct UaTile {
+  static constexpr int PITCH = HDP == 32 ? 64 : 128;                 // bytes per row
+  static constexpr uint32_t LAYOUT = HDP == 32 ? 4u : 2u;            // descriptor layout type
+  static constexpr uint32_t SBO = 8 * PITCH / 16;                    // 8-row group stride, 16-byte units
+  static constexpr uint32_t MN_KADV = 16 * PITCH / 16;               // MN-major: 16 K-rows per UMMA_K step
+  __device__ static __forceinline__ uint32_t chunk(int r, int c) {   // physical 16-byte chunk of logical chunk c
+    return HDP == 32 ? (uint32_t)(c ^ ((r >> 1) & 3)) : (uint32_t)(c ^ (r & 7));
+  }
+  __device__ static __forceinline__ uint64_t kmajor(uint32_t saddr) { return ua_desc(saddr, 1, SBO, LAYOUT); }
+  __device__ static __forceinline__ uint64_t mnmajor(uint32_t saddr) { return ua_desc(saddr, 512, SBO, LAYOUT); }
+};
 __device__ __forceinline__ void ua_cp16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
 }
@@ -71,8 +86,7 @@ __device__ __forceinline__ void ua_st32(uint32_t taddr, const float* v) {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-// One warp stages ROWS rows x HDP bf16 (hd real columns, rest zero) into a SWIZZLE_128B tile:
-// 16-byte chunk c of row r lands at r*128 + ((c ^ (r & 7)) << 4).
+// `nthreads` threads stage ROWS rows x HDP bf16 (hd real columns, rest zero) into a swizzled UaTile<HDP> tile.
 template <int HDP, int ROWS = 128>
 __device__ __forceinline__ void ua_stage(uint32_t tile, const bf16* __restrict__ src, int64_t row_stride, int row0,
                                          int nrows_total, int hd, int tid, int nthreads = 32) {
@@ -80,7 +94,7 @@ __device__ __forceinline__ void ua_stage(uint32_t tile, const bf16* __restrict__
   const int hd_ch = hd / 8;
   for (int e = tid; e < ROWS * CH; e += nthreads) {
     const int r = e / CH, c = e % CH;
-    const uint32_t dst = tile + r * 128 + ((c ^ (r & 7)) << 4);
+    const uint32_t dst = tile + r * UaTile<HDP>::PITCH + (UaTile<HDP>::chunk(r, c) << 4);
     if (row0 + r < nrows_total && c < hd_ch) {
       ua_cp16(dst, src + (int64_t)(row0 + r) * row_stride + c * 8);
     } else {

@@ -224,26 +224,31 @@ fa_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __res
 }
 
 // ============================================================================ backward
-// delta[b,h,i] = sum_d dO . O  (one warp per (b, i, h))
-__global__ void fa_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, float* __restrict__ delta,
-                                int B, int N, int H, int hd) {
+// delta[b,h,i] = sum_d dO . O  -- one THREAD per (b, i, h): a head slice is hd contiguous bf16 (48..256 B),
+// read as 16-byte vectors; consecutive threads take consecutive heads, i.e. consecutive memory.
+__global__ void __launch_bounds__(256)
+fa_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, float* __restrict__ delta,
+                int B, int N, int H, int hd) {
   const int64_t total = (int64_t)B * N * H;
-  const int lane = threadIdx.x & 31;
-  for (int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; w < total; w += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+  for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < total; w += (int64_t)gridDim.x * blockDim.x) {
     const int h = (int)(w % H);
     const int64_t bn = w / H;
     const int i = (int)(bn % N), b = (int)(bn / N);
-    const bf16* o = out + (bn * H + h) * hd;
-    const bf16* g = dout + (bn * H + h) * hd;
+    const bf16* o = out + w * hd;
+    const bf16* g = dout + w * hd;
     float s = 0.f;
-    for (int d = lane * 2; d < hd; d += 64) {
-      float a0, a1, b0, b1;
-      unpack_bf16x2(*reinterpret_cast<const uint32_t*>(o + d), a0, a1);
-      unpack_bf16x2(*reinterpret_cast<const uint32_t*>(g + d), b0, b1);
-      s += a0 * b0 + a1 * b1;
+    if ((hd & 7) == 0) {
+      for (int d = 0; d < hd; d += 8) {
+        float a[8], c[8];
+        load8<bf16>(o + d, a);
+        load8<bf16>(g + d, c);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s = fmaf(a[e], c[e], s);
+      }
+    } else {
+      for (int d = 0; d < hd; ++d) s = fmaf(__bfloat162float(o[d]), __bfloat162float(g[d]), s);
     }
-    s = warp_sum(s);
-    if (lane == 0) delta[((int64_t)b * H + h) * N + i] = s;
+    delta[((int64_t)b * H + h) * N + i] = s;
   }
 }
 
@@ -465,8 +470,8 @@ static int fwd_launch(const bf16* qkv, bf16* out, float* lse, int B, int N, int 
 
 // delta[b,h,i] = sum_d dO . O into `delta` ([B, H, N] fp32); shared with the tcgen05 backward.
 int avj_attention_delta(const void* out, const void* dout, float* delta, int B, int N, int H, int hd, cudaStream_t s) {
-  const int64_t warps = (int64_t)B * N * H;
-  int grid = (int)((warps + 7) / 8);
+  const int64_t threads = (int64_t)B * N * H;
+  int grid = (int)((threads + 255) / 256);
   const int cap = avj_num_sms() * 16;
   if (grid > cap) grid = cap;
   fa_delta_kernel<<<grid, 256, 0, s>>>((const bf16*)out, (const bf16*)dout, delta, B, N, H, hd);

@@ -31,8 +31,16 @@
 #define UA_BN 128
 #define UA_THREADS 256
 #define UA_LOADERS 96             // cp.async path: warps 0, 2, 3
-#define UA_TILE_BYTES (128 * 128)                 // 128 rows x 128 B (one swizzle atom wide)
-#define UA_SMEM_BYTES (UA_TILE_BYTES * (1 + 2 + 2 + 2) + 256)   // Q, K[2], V[2], P(2 atoms) + barriers
+#define UA_P_TILE (128 * 128)                     // one 64-key atom of P: 128 rows x 128 B
+
+// K/V ring depth: the stage of tile t is released by PV(t), so 2 stages expose the full load latency of
+// tile t+2 every step.  hd <= 32 tiles have 64-byte rows (UaTile) and afford 4 stages next to a second CTA.
+template <int HDP> struct UaSmem {
+  static constexpr int NST = HDP == 32 ? 4 : 2;
+  static constexpr uint32_t TILE = 128 * UaTile<HDP>::PITCH;
+  static constexpr uint32_t Q = 0, K = TILE, V = K + NST * TILE, P = V + NST * TILE, BARS = P + 2 * UA_P_TILE,
+                            TOTAL = BARS + 256;
+};
 #define UA_TMEM_COLS 256
 #define UA_O_COL 128
 
@@ -44,18 +52,22 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
                    float* __restrict__ lse, int N, int H, int hd, float scale_log2) {
   extern __shared__ __align__(1024) uint8_t ua_raw[];
   const uint32_t base = ua_smem(ua_raw);
-  const uint32_t sQ = base;
-  const uint32_t sK = sQ + UA_TILE_BYTES;            // [2]
-  const uint32_t sV = sK + 2 * UA_TILE_BYTES;        // [2]
-  const uint32_t sP = sV + 2 * UA_TILE_BYTES;        // 2 atoms of 64 keys
-  const uint32_t bars = sP + 2 * UA_TILE_BYTES;
-  const uint32_t kv_full = bars;            // [2] count 32
-  const uint32_t kv_empty = bars + 16;      // [2] count 1
-  const uint32_t s_full = bars + 32;        // count 1
-  const uint32_t s_free = bars + 40;        // count 128
-  const uint32_t p_full = bars + 48;        // count 128
-  const uint32_t o_done = bars + 56;        // count 1
-  const uint32_t tmem_slot = bars + 64;
+  using L = UaSmem<HDP>;
+  using TL = UaTile<HDP>;
+  constexpr int NST = L::NST;
+  constexpr uint32_t UA_TILE_BYTES = L::TILE;
+  const uint32_t sQ = base + L::Q;
+  const uint32_t sK = base + L::K;                   // [NST]
+  const uint32_t sV = base + L::V;                   // [NST]
+  const uint32_t sP = base + L::P;                   // 2 atoms of 64 keys
+  const uint32_t bars = base + L::BARS;
+  const uint32_t kv_full = bars;            // [NST <= 4]
+  const uint32_t kv_empty = bars + 32;      // [NST <= 4] count 1
+  const uint32_t s_full = bars + 64;        // count 1
+  const uint32_t s_free = bars + 72;        // count 128
+  const uint32_t p_full = bars + 80;        // count 128
+  const uint32_t o_done = bars + 88;        // count 1
+  const uint32_t tmem_slot = bars + 96;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(ua_raw + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -68,8 +80,7 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
 
   if (threadIdx.x == 0) {
     if (base & 1023u) __trap();                      // SWIZZLE_128B tiles need 1024-byte alignment
-    ua_mbar_init(kv_full, TMA ? 1 : UA_LOADERS); ua_mbar_init(kv_full + 8, TMA ? 1 : UA_LOADERS);
-    ua_mbar_init(kv_empty, 1); ua_mbar_init(kv_empty + 8, 1);
+    for (int i = 0; i < NST; ++i) { ua_mbar_init(kv_full + 8 * i, TMA ? 1 : UA_LOADERS); ua_mbar_init(kv_empty + 8 * i, 1); }
     ua_mbar_init(s_full, 1); ua_mbar_init(s_free, 128); ua_mbar_init(p_full, 128); ua_mbar_init(o_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -92,8 +103,8 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
         const int cq = h * hd, ck = (H + h) * hd, cv = (2 * H + h) * hd;
         for (int t = 0; t < T; ++t) {
-          const int st = t & 1;
-          if (t >= 2) ua_mbar_wait(kv_empty + 8 * st, ((t >> 1) & 1) ^ 1);
+          const int st = t % NST;
+          if (t >= NST) ua_mbar_wait(kv_empty + 8 * st, ((t / NST) & 1) ^ 1);
           const uint32_t fb = kv_full + 8 * st;
           ua_expect_tx(fb, (t == 0 ? 3 : 2) * UA_TILE_BYTES);
           if (t == 0) ua_tma3d(sQ, &tmap, fb, cq, q0, b);
@@ -102,58 +113,58 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
         }
       }
     } else {
-      // gather tile t+1 while the tensor core works on tile t.  kv_full[t] must be signalled BEFORE
-      // waiting for the stage of tile t+1 to drain (the MMA warp issues S(t+1) ahead of PV(t)).
+      // up to NST-1 K/V tiles are kept in flight.  kv_full[j] is signalled BEFORE waiting for the stage of
+      // tile t to drain (the MMA warp issues S(j) ahead of PV(t-NST)); the opposite order would deadlock.
       ua_stage<HDP>(sQ, qb, rs, q0, N, hd, ld_tid, UA_LOADERS);
-      ua_stage<HDP>(sK, kb, rs, 0, N, hd, ld_tid, UA_LOADERS);
-      ua_stage<HDP>(sV, vb, rs, 0, N, hd, ld_tid, UA_LOADERS);
-      asm volatile("cp.async.commit_group;" ::: "memory");
       for (int t = 0; t < T; ++t) {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        ua_fence_async_smem();
-        ua_mbar_arrive(kv_full + 8 * (t & 1));
-        if (t + 1 < T) {
-          const int s1 = (t + 1) & 1;
-          if (t + 1 >= 2) ua_mbar_wait(kv_empty + 8 * s1, (((t + 1) >> 1) & 1) ^ 1);
-          ua_stage<HDP>(sK + s1 * UA_TILE_BYTES, kb, rs, (t + 1) * UA_BN, N, hd, ld_tid, UA_LOADERS);
-          ua_stage<HDP>(sV + s1 * UA_TILE_BYTES, vb, rs, (t + 1) * UA_BN, N, hd, ld_tid, UA_LOADERS);
-          asm volatile("cp.async.commit_group;" ::: "memory");
+        const int st = t % NST;
+        if (t >= NST - 1) {
+          asm volatile("cp.async.wait_group %0;" ::"n"(NST - 2) : "memory");
+          ua_fence_async_smem();
+          ua_mbar_arrive(kv_full + 8 * ((t - (NST - 1)) % NST));
         }
+        if (t >= NST) ua_mbar_wait(kv_empty + 8 * st, ((t / NST) & 1) ^ 1);
+        ua_stage<HDP>(sK + st * UA_TILE_BYTES, kb, rs, t * UA_BN, N, hd, ld_tid, UA_LOADERS);
+        ua_stage<HDP>(sV + st * UA_TILE_BYTES, vb, rs, t * UA_BN, N, hd, ld_tid, UA_LOADERS);
+        asm volatile("cp.async.commit_group;" ::: "memory");
       }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      ua_fence_async_smem();
+      for (int j = max(0, T - (NST - 1)); j < T; ++j) ua_mbar_arrive(kv_full + 8 * (j % NST));
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
     if (lane == 0) {
       const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UA_BN >> 3) << 17) | ((uint32_t)(UA_BM >> 4) << 24);
       const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HDP >> 3) << 17) | ((uint32_t)(UA_BM >> 4) << 24);
-      const uint64_t qd = ua_desc(sQ, 1, 64);
+      const uint64_t qd = TL::kmajor(sQ);
       auto issue_s = [&](int t) {
-        const uint64_t kd = ua_desc(sK + (t & 1) * UA_TILE_BYTES, 1, 64);
+        const uint64_t kd = TL::kmajor(sK + (t % NST) * UA_TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < HDP / 16; ++k) ua_mma(tmem, qd + 2 * k, kd + 2 * k, idesc_s, k > 0 ? 1u : 0u);
         ua_commit(s_full);
       };
-      ua_mbar_wait(kv_full, 0);
+      ua_mbar_wait(kv_full, 0);   // tile 0 (and Q)
       ua_fence_after();
       issue_s(0);
       for (int t = 0; t < T; ++t) {
         if (t + 1 < T) {
-          ua_mbar_wait(kv_full + 8 * ((t + 1) & 1), ((t + 1) >> 1) & 1);
+          ua_mbar_wait(kv_full + 8 * ((t + 1) % NST), ((t + 1) / NST) & 1);
           ua_mbar_wait(s_free, t & 1);                 // softmax has S[t] in registers
           ua_fence_after();
           issue_s(t + 1);
         }
         ua_mbar_wait(p_full, t & 1);
         ua_fence_after();
-        const uint32_t vt = sV + (t & 1) * UA_TILE_BYTES;
+        const uint32_t vt = sV + (t % NST) * UA_TILE_BYTES;
 #pragma unroll
         for (int k = 0; k < UA_BN / 16; ++k) {
-          const uint64_t pd = ua_desc(sP + (k >> 2) * UA_TILE_BYTES, 1, 64) + 2 * (k & 3);
-          const uint64_t vd = ua_desc(vt, 512, 64) + 128 * k;        // MN-major: 16 keys = 2048 B per step
+          const uint64_t pd = ua_desc(sP + (k >> 2) * UA_P_TILE, 1, 64) + 2 * (k & 3);
+          const uint64_t vd = TL::mnmajor(vt) + TL::MN_KADV * k;     // MN-major: 16 keys per step
           ua_mma(tmem + UA_O_COL, pd, vd, idesc_o, (t > 0 || k > 0) ? 1u : 0u);
         }
         ua_commit(o_done);
-        ua_commit(kv_empty + 8 * (t & 1));
+        ua_commit(kv_empty + 8 * (t % NST));
       }
     }
   }
@@ -191,8 +202,8 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
       uint32_t pk[64];
 #pragma unroll
       for (int j = 0; j < 128; j += 2) {
-        const float p0 = exp2f(fmaf(s[j], scale_log2, -mb));
-        const float p1 = exp2f(fmaf(s[j + 1], scale_log2, -mb));
+        const float p0 = ua_exp2(fmaf(s[j], scale_log2, -mb));
+        const float p1 = ua_exp2(fmaf(s[j + 1], scale_log2, -mb));
         rsum += p0 + p1;
         pk[j >> 1] = pack_bf16x2(p0, p1);
       }
@@ -202,7 +213,7 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
       ua_fence_after();
 #pragma unroll
       for (int c = 0; c < 16; ++c) {                                 // 16 chunks of 8 keys
-        const uint32_t dst = sP + (c >> 3) * UA_TILE_BYTES + row * 128 + (((c & 7) ^ (row & 7)) << 4);
+        const uint32_t dst = sP + (c >> 3) * UA_P_TILE + row * 128 + (((c & 7) ^ (row & 7)) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
                      "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
       }
@@ -302,7 +313,7 @@ template <int HDP, bool TMA>
 static int ua_launch(const bf16* qkv, bf16* out, float* lse, int B, int N, int H, int hd, float scale, cudaStream_t s) {
   static bool set = false;
   if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(fa_fwd_umma_kernel<HDP, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, UA_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(fa_fwd_umma_kernel<HDP, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UaSmem<HDP>::TOTAL);
     AVJ_CHECK(e == cudaSuccess, "cudaFuncSetAttribute(fa_fwd_umma_kernel) failed: %s", cudaGetErrorString(e));
     // two CTAs per SM need the full 228 KB shared-memory carve-out
     cudaFuncSetAttribute(fa_fwd_umma_kernel<HDP, TMA>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -315,7 +326,7 @@ static int ua_launch(const bf16* qkv, bf16* out, float* lse, int B, int N, int H
     if (rc) return rc;
   }
   dim3 grid((N + UA_BM - 1) / UA_BM, H, B);
-  fa_fwd_umma_kernel<HDP, TMA><<<grid, UA_THREADS, UA_SMEM_BYTES, s>>>(map, qkv, out, lse, N, H, hd, scale * 1.4426950408889634f);
+  fa_fwd_umma_kernel<HDP, TMA><<<grid, UA_THREADS, UaSmem<HDP>::TOTAL, s>>>(map, qkv, out, lse, N, H, hd, scale * 1.4426950408889634f);
   AVJ_LAUNCH_CHECK();
   return 0;
 }

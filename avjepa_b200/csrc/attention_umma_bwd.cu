@@ -42,18 +42,23 @@
 #define UB_BN 64
 #define UB_THREADS 256
 #define UB_LOADERS 96            // cp.async path: warps 0, 2, 3
-#define UB_ROW_TILE (128 * 128)      // 128 rows x 128 B
-#define UB_COL_TILE (64 * 128)       // 64 rows x 128 B
 #define UB_TMEM_COLS 256
 #define UB_T2_COL 64
 #define UB_O1_COL 128
 #define UB_O2_COL 192
+#define UB_PD_TILE (128 * 128)       // P^T / dS^T: 128 rows x 64 streamed columns bf16 (always 128-byte rows)
 
-template <bool KV> struct UbSmem {
-  static constexpr uint32_t R1 = 0, R2 = UB_ROW_TILE, C1 = 2 * UB_ROW_TILE, C2 = C1 + 2 * UB_COL_TILE,
-                            DS = C2 + 2 * UB_COL_TILE, P = DS + UB_ROW_TILE,
-                            STAT = KV ? P + UB_ROW_TILE : P,            // [2 stages][lse2 64 | delta 64] floats
-                            BARS = STAT + (KV ? 1024 : 0), TOTAL = BARS + 128;
+// Streamed-tile ring depth.  The stage of tile t is only released by the OUTPUT MMAs of step t, so with 2
+// stages the load of tile t+2 starts when step t ends and its full L2 latency is exposed every step; 3-4
+// stages issue it one or two steps earlier.  hd <= 32 tiles are half the size (64-byte rows) so 4 stages
+// fit next to a second CTA; at hd = 64 the dK/dV pass only has room for 2.
+template <int HDP, bool KV> struct UbSmem {
+  static constexpr int NST = HDP == 32 ? 4 : (KV ? 2 : 3);
+  static constexpr uint32_t ROW_TILE = 128 * UaTile<HDP>::PITCH, COL_TILE = 64 * UaTile<HDP>::PITCH;
+  static constexpr uint32_t R1 = 0, R2 = ROW_TILE, C1 = 2 * ROW_TILE, C2 = C1 + NST * COL_TILE,
+                            DS = C2 + NST * COL_TILE, P = DS + UB_PD_TILE,
+                            STAT = KV ? P + UB_PD_TILE : P,             // [NST][lse2 64 | delta 64] floats
+                            BARS = STAT + (KV ? NST * 512 : 0), TOTAL = BARS + 128;
 };
 
 template <int HDP, bool TMA, bool KV>
@@ -62,20 +67,22 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
                    const __grid_constant__ CUtensorMap map_do, const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                    const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv,
                    int N, int H, int hd, float scale, float scale_log2) {
-  using L = UbSmem<KV>;
+  using L = UbSmem<HDP, KV>;
+  using TL = UaTile<HDP>;
+  constexpr int NST = L::NST;
   extern __shared__ __align__(1024) uint8_t ub_raw[];
   const uint32_t base = ua_smem(ub_raw);
   const uint32_t sR1 = base + L::R1, sR2 = base + L::R2, sC1 = base + L::C1, sC2 = base + L::C2;
   const uint32_t sDS = base + L::DS, sP = base + L::P;
   const uint32_t bars = base + L::BARS;
-  const uint32_t c_full = bars;             // [2]
-  const uint32_t c_empty = bars + 16;       // [2]
-  const uint32_t t_full = bars + 32;
-  const uint32_t t_free = bars + 40;
-  const uint32_t p_full = bars + 48;
-  const uint32_t o_done = bars + 56;
-  const uint32_t tmem_slot = bars + 64;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(ub_raw + L::BARS + 64);
+  const uint32_t c_full = bars;             // [NST <= 4]
+  const uint32_t c_empty = bars + 32;       // [NST <= 4]
+  const uint32_t t_full = bars + 64;
+  const uint32_t t_free = bars + 72;
+  const uint32_t p_full = bars + 80;
+  const uint32_t o_done = bars + 88;
+  const uint32_t tmem_slot = bars + 96;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(ub_raw + L::BARS + 96);
   float* stat = reinterpret_cast<float*>(ub_raw + L::STAT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -92,8 +99,7 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
 
   if (threadIdx.x == 0) {
     if (base & 1023u) __trap();
-    ua_mbar_init(c_full, TMA ? 1 : UB_LOADERS); ua_mbar_init(c_full + 8, TMA ? 1 : UB_LOADERS);
-    ua_mbar_init(c_empty, 1); ua_mbar_init(c_empty + 8, 1);
+    for (int i = 0; i < NST; ++i) { ua_mbar_init(c_full + 8 * i, TMA ? 1 : UB_LOADERS); ua_mbar_init(c_empty + 8 * i, 1); }
     ua_mbar_init(t_full, 1); ua_mbar_init(t_free, 128); ua_mbar_init(p_full, 128); ua_mbar_init(o_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -122,15 +128,16 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
       else    ua_stage<HDP, 128>(sR2, dob, os, r0, N, hd, ld_tid, ld_n);
     }
     for (int t = 0; t < T; ++t) {
-      const int st = t & 1;
-      if (!TMA && t > 0) {
-        // tile t-1 has landed: signal it BEFORE waiting for stage `st` to drain -- the MMA warp issues
-        // scores(t-1) ahead of outputs(t-2), so the opposite order would deadlock.
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      const int st = t % NST;
+      if (!TMA && t >= NST - 1) {
+        // tile j = t-(NST-1) has landed once at most NST-2 copy groups are pending.  It is signalled BEFORE
+        // waiting for stage `st` to drain: the MMA warp issues scores(j) ahead of outputs(t-NST), so the
+        // opposite order would deadlock.
+        asm volatile("cp.async.wait_group %0;" ::"n"(NST - 2) : "memory");
         ua_fence_async_smem();
-        ua_mbar_arrive(c_full + 8 * ((t - 1) & 1));
+        ua_mbar_arrive(c_full + 8 * ((t - (NST - 1)) % NST));
       }
-      if (t >= 2) ua_mbar_wait(c_empty + 8 * st, ((t >> 1) & 1) ^ 1);
+      if (t >= NST) ua_mbar_wait(c_empty + 8 * st, ((t / NST) & 1) ^ 1);
       if (KV) {                                               // per-column statistics of this query tile
         for (int i = ld_tid; i < UB_BN; i += ld_n) {
           const int qi = t * UB_BN + i;
@@ -139,11 +146,11 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
         }
         __syncwarp();
       }
-      const uint32_t c1 = sC1 + st * UB_COL_TILE, c2 = sC2 + st * UB_COL_TILE;
+      const uint32_t c1 = sC1 + st * L::COL_TILE, c2 = sC2 + st * L::COL_TILE;
       if (TMA) {
         if (lane == 0) {
           const uint32_t fb = c_full + 8 * st;
-          ua_expect_tx(fb, 2 * UB_COL_TILE + (t == 0 ? 2 * UB_ROW_TILE : 0));
+          ua_expect_tx(fb, 2 * L::COL_TILE + (t == 0 ? 2 * L::ROW_TILE : 0));
           if (t == 0) {
             ua_tma3d(sR1, &map_qkv128, fb, c_r1, r0, b);
             if (KV) ua_tma3d(sR2, &map_qkv128, fb, (2 * H + h) * hd, r0, b);
@@ -163,17 +170,17 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
     if (!TMA) {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       ua_fence_async_smem();
-      ua_mbar_arrive(c_full + 8 * ((T - 1) & 1));
+      for (int j = max(0, T - (NST - 1)); j < T; ++j) ua_mbar_arrive(c_full + 8 * (j % NST));
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
     if (lane == 0) {
       const uint32_t idesc_t = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UB_BN >> 3) << 17) | ((uint32_t)(UB_BM >> 4) << 24);
       const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HDP >> 3) << 17) | ((uint32_t)(UB_BM >> 4) << 24);
-      const uint64_t r1d = ua_desc(sR1, 1, 64), r2d = ua_desc(sR2, 1, 64);
+      const uint64_t r1d = TL::kmajor(sR1), r2d = TL::kmajor(sR2);
       auto issue_scores = [&](int t) {
-        const uint64_t c1d = ua_desc(sC1 + (t & 1) * UB_COL_TILE, 1, 64);
-        const uint64_t c2d = ua_desc(sC2 + (t & 1) * UB_COL_TILE, 1, 64);
+        const uint64_t c1d = TL::kmajor(sC1 + (t % NST) * L::COL_TILE);
+        const uint64_t c2d = TL::kmajor(sC2 + (t % NST) * L::COL_TILE);
 #pragma unroll
         for (int k = 0; k < HDP / 16; ++k) ua_mma(tmem, r1d + 2 * k, c1d + 2 * k, idesc_t, k > 0 ? 1u : 0u);
 #pragma unroll
@@ -185,30 +192,30 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
       issue_scores(0);
       for (int t = 0; t < T; ++t) {
         if (t + 1 < T) {
-          ua_mbar_wait(c_full + 8 * ((t + 1) & 1), ((t + 1) >> 1) & 1);
+          ua_mbar_wait(c_full + 8 * ((t + 1) % NST), ((t + 1) / NST) & 1);
           ua_mbar_wait(t_free, t & 1);                       // both score tiles of step t are in registers
           ua_fence_after();
           issue_scores(t + 1);
         }
         ua_mbar_wait(p_full, t & 1);
         ua_fence_after();
-        const uint32_t c1 = sC1 + (t & 1) * UB_COL_TILE, c2 = sC2 + (t & 1) * UB_COL_TILE;
+        const uint32_t c1 = sC1 + (t % NST) * L::COL_TILE, c2 = sC2 + (t % NST) * L::COL_TILE;
         const uint32_t accum0 = t > 0 ? 1u : 0u;
         const uint64_t dsd = ua_desc(sDS, 1, 64);
-        const uint64_t c1m = ua_desc(c1, 512, 64);           // MN-major view: 16 rows = 2048 B per K step
+        const uint64_t c1m = TL::mnmajor(c1);                // MN-major view: 16 streamed rows per K step
         if (KV) {
           const uint64_t pd = ua_desc(sP, 1, 64);
-          const uint64_t c2m = ua_desc(c2, 512, 64);
+          const uint64_t c2m = TL::mnmajor(c2);
 #pragma unroll
-          for (int k = 0; k < UB_BN / 16; ++k) ua_mma(tmem + UB_O1_COL, pd + 2 * k, c2m + 128 * k, idesc_o, (accum0 | (k > 0)) ? 1u : 0u);   // dV += P^T dO
+          for (int k = 0; k < UB_BN / 16; ++k) ua_mma(tmem + UB_O1_COL, pd + 2 * k, c2m + TL::MN_KADV * k, idesc_o, (accum0 | (k > 0)) ? 1u : 0u);   // dV += P^T dO
 #pragma unroll
-          for (int k = 0; k < UB_BN / 16; ++k) ua_mma(tmem + UB_O2_COL, dsd + 2 * k, c1m + 128 * k, idesc_o, (accum0 | (k > 0)) ? 1u : 0u);  // dK += dS^T Q
+          for (int k = 0; k < UB_BN / 16; ++k) ua_mma(tmem + UB_O2_COL, dsd + 2 * k, c1m + TL::MN_KADV * k, idesc_o, (accum0 | (k > 0)) ? 1u : 0u);  // dK += dS^T Q
         } else {
 #pragma unroll
-          for (int k = 0; k < UB_BN / 16; ++k) ua_mma(tmem + UB_O1_COL, dsd + 2 * k, c1m + 128 * k, idesc_o, (accum0 | (k > 0)) ? 1u : 0u);  // dQ += dS K
+          for (int k = 0; k < UB_BN / 16; ++k) ua_mma(tmem + UB_O1_COL, dsd + 2 * k, c1m + TL::MN_KADV * k, idesc_o, (accum0 | (k > 0)) ? 1u : 0u);  // dQ += dS K
         }
         ua_commit(o_done);
-        ua_commit(c_empty + 8 * (t & 1));
+        ua_commit(c_empty + 8 * (t % NST));
       }
     }
   }
@@ -231,8 +238,8 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
       ua_fence_before();
       ua_mbar_arrive(t_free);
       uint32_t pk_p[KV ? 32 : 1], pk_d[32];
-      const float* st_l2 = stat + (t & 1) * 128;
-      if (KV) ua_mbar_wait(c_full + 8 * (t & 1), (t >> 1) & 1);   // acquire the loader's lse/delta stores
+      const float* st_l2 = stat + (t % NST) * 128;
+      if (KV) ua_mbar_wait(c_full + 8 * (t % NST), (t / NST) & 1);   // acquire the loader's lse/delta stores
 #pragma unroll
       for (int j = 0; j < 64; j += 4) {
         float l2[4], dl[4];
@@ -319,7 +326,7 @@ template <int HDP, bool TMA, bool KV>
 static int ub_launch(const CUtensorMap& m128, const CUtensorMap& m64, const CUtensorMap& mdo, const bf16* qkv, const bf16* dout,
                      const float* lse, const float* delta, bf16* dqkv, int B, int N, int H, int hd, float scale, cudaStream_t s) {
   static bool set = false;
-  const int smem = (int)UbSmem<KV>::TOTAL;
+  const int smem = (int)UbSmem<HDP, KV>::TOTAL;
   if (!set) {
     cudaError_t e = cudaFuncSetAttribute(fa_bwd_umma_kernel<HDP, TMA, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     AVJ_CHECK(e == cudaSuccess, "cudaFuncSetAttribute(fa_bwd_umma_kernel) failed: %s", cudaGetErrorString(e));

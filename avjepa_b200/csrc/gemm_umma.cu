@@ -619,7 +619,7 @@ int avj_gemm_umma(int layout, const void* A, const void* B, void* C, int M, int 
   else               rc = get_tensor_map(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, UG_BK, &mb);
   if (rc) return rc;
 
-  static const uint32_t l2pf = env_u32("AVJ_GEMM_L2PF", 1);
+  static const uint32_t l2pf = env_u32("AVJ_GEMM_L2PF", 0);
   p.l2_prefetch = (int)l2pf;
   // ---- epilogue specialisation
   const bool adds = ep.residual || ep.pos || ep.accumulate;

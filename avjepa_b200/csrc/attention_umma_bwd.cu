@@ -142,7 +142,7 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
         for (int i = ld_tid; i < UB_BN; i += ld_n) {
           const int qi = t * UB_BN + i;
           stat[st * 128 + i] = qi < N ? lse_bh[qi] * 1.4426950408889634f : 0.f;
-          stat[st * 128 + 64 + i] = qi < N ? delta_bh[qi] : 0.f;
+          stat[st * 128 + 64 + i] = qi < N ? delta_bh[qi] * scale : 0.f;     // pre-scaled: dS = P (scale dP - scale delta)
         }
         __syncwarp();
       }
@@ -227,7 +227,7 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
     const uint32_t t_1 = tmem + ((uint32_t)(q * 32) << 16);
     const int ri = r0 + row;
     float my_l2 = 0.f, my_dl = 0.f;
-    if (!KV && ri < N) { my_l2 = lse_bh[ri] * 1.4426950408889634f; my_dl = delta_bh[ri]; }
+    if (!KV && ri < N) { my_l2 = lse_bh[ri] * 1.4426950408889634f; my_dl = delta_bh[ri] * scale; }
     for (int t = 0; t < T; ++t) {
       ua_mbar_wait(t_full, t & 1);
       ua_fence_after();
@@ -256,7 +256,7 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           p[e] = ua_exp2(fmaf(s[j + e], scale_log2, -l2[e]));
-          ds[e] = p[e] * (dp[j + e] - dl[e]) * scale;
+          ds[e] = p[e] * fmaf(dp[j + e], scale, -dl[e]);
         }
         if constexpr (KV) { pk_p[j >> 1] = pack_bf16x2(p[0], p[1]); pk_p[(j >> 1) + 1] = pack_bf16x2(p[2], p[3]); }
         pk_d[j >> 1] = pack_bf16x2(ds[0], ds[1]); pk_d[(j >> 1) + 1] = pack_bf16x2(ds[2], ds[3]);

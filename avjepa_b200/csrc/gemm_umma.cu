@@ -40,7 +40,6 @@ struct UmmaParams {
   int split_k;           // >= 1
   int kb_per_split;
   int a_mn_major, b_mn_major;
-  int l2_prefetch;       // bulk-prefetch next tile's epilogue operands into L2
   uint32_t mn_lbo, mn_sbo, mn_kadv;   // MN-major descriptor fields / k-advance (16 B units)
   void* C;
   avj_epilogue ep;
@@ -143,6 +142,198 @@ __device__ __forceinline__ float4 lds_f4(uint32_t a) {
 }
 __device__ __forceinline__ void sts_f4(uint32_t a, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// One accumulator tile (this warp's 32 rows x [c_lo, c_hi) columns) through the fused epilogue.
+// `wait_full` blocks until the tile's MMAs have retired, `release` signals that the TMEM buffer is drained.
+template <int EPI, class WaitFull, class Release>
+__device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int row_base, int n_blk, uint32_t taddr, uint32_t stg,
+                                              int lane, int c_lo, int c_hi, WaitFull wait_full, Release release) {
+  const avj_epilogue& ep = p.ep;
+  const int cols_half = c_hi - c_lo;
+  const int sub = lane >> 3, c4 = lane & 7;        // transposed phase: row i*4+sub, float4 column c4
+  uint32_t raw[32];
+
+  if (EPI == EPI_PLAIN || EPI == EPI_GELU || EPI == EPI_DACT) {
+    // ---------------- direct: thread == row, 32 consecutive columns per step ----------------
+    // the warp's bias segment goes to shared memory once per tile (broadcast reads afterwards)
+    const bool has_bias = (EPI != EPI_DACT) && ep.bias != nullptr;
+    if (has_bias) {
+      __syncwarp();                               // every lane is done with the previous tile's bias
+      if (lane * 4 < cols_half) sts_f4(stg + lane * 16, ld_f4(ep.bias + n_blk * p.block_n + c_lo + lane * 4));
+      __syncwarp();
+    }
+    const int64_t row = row_base + lane;
+    const bool row_ok = row < p.M;
+    const int64_t prow = row_ok ? map_row(ep.out_map, row) : 0;
+    wait_full();
+    tmem_ld32_issue(taddr + c_lo, raw);
+    for (int c = c_lo; c < c_hi; c += 32) {
+      const int n0 = n_blk * p.block_n + c;
+      uint4 aux[4];
+      if (EPI == EPI_DACT) {
+        const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.dact_aux) + row * (int64_t)p.N + n0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) aux[j] = row_ok ? ap[j] : make_uint4(0u, 0u, 0u, 0u);
+      }
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+      if (c + 32 < c_hi) {
+        tmem_ld32_issue(taddr + c + 32, raw);
+      } else {
+        release();
+      }
+      if (has_bias) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = lds_f4(stg + (c - c_lo + j * 4) * 4);
+          v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+        }
+      }
+      if (!row_ok) continue;
+      if (EPI == EPI_GELU) {
+        if (ep.pre_out) {
+          uint4* pp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.pre_out) + row * (int64_t)p.N + n0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            pp[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                               pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = gelu_fwd<true>(v[i]);
+      }
+      if (EPI == EPI_DACT) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t w[4] = {aux[j].x, aux[j].y, aux[j].z, aux[j].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x0, x1;
+            unpack_bf16x2(w[e], x0, x1);
+            v[8 * j + 2 * e] *= gelu_bwd<true>(x0);
+            v[8 * j + 2 * e + 1] *= gelu_bwd<true>(x1);
+          }
+        }
+      }
+      if (ep.out_dtype == AVJ_F32) {
+        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + prow * (int64_t)p.ldc + n0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      } else {
+        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.C) + prow * (int64_t)p.ldc + n0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          op[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                             pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+      }
+    }
+  } else if (EPI == EPI_GENERIC) {
+    // ---------------- generic direct path: every epilogue field evaluated at run time ----------------
+    wait_full();
+    tmem_ld32_issue(taddr + c_lo, raw);
+    const int64_t row = row_base + lane;
+    const bool row_ok = row < p.M;
+    for (int c = c_lo; c < c_hi; c += 32) {
+      const int n0 = n_blk * p.block_n + c;
+      float add[32];
+      if (p.split_k == 1 && row_ok) epilogue_prefetch<32>(ep, p.C, p.ldc, p.N, row, n0, add);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+      if (c + 32 < c_hi) {
+        tmem_ld32_issue(taddr + c + 32, raw);
+      } else {
+        release();
+      }
+      if (row_ok) {
+        if (p.split_k > 1) {
+          float* out = reinterpret_cast<float*>(p.C) + map_row(ep.out_map, row) * (int64_t)p.ldc + n0;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) atomicAdd(reinterpret_cast<float4*>(out + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+        } else {
+          epilogue_apply_store<bf16, 32, true>(ep, p.C, p.ldc, p.N, row, n0, v, add);
+        }
+      }
+    }
+  } else {
+    // ---------------- transposed: coalesced 4 rows x 128 B per warp instruction, fp32 C ----------------
+    int prow[8];                                   // physical C row of my 8 rows, -1 = past M
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = row_base + i * 4 + sub;
+      prow[i] = r < p.M ? (int)map_row(ep.out_map, r) : -1;
+    }
+    wait_full();
+    tmem_ld32_issue(taddr + c_lo, raw);
+    for (int c = c_lo; c < c_hi; c += 32) {
+      const int n = n_blk * p.block_n + c + c4 * 4;
+      // ---- addends that do not depend on the accumulator: ALL loads are issued back to back (rows past
+      // M are clamped to a valid row and discarded) so one chunk costs one memory round trip, and they
+      // are in flight while the TMEM load completes
+      float4 add[8], add2[8];
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool two = ep.accumulate && (ep.residual || ep.pos);
+      if (p.split_k == 1) {
+        if (ep.bias) b4 = ld_f4(ep.bias + n);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { add[i] = make_float4(0.f, 0.f, 0.f, 0.f); add2[i] = add[i]; }
+        if (ep.residual) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) add[i] = ld_f4(ep.residual + (int64_t)max(prow[i], 0) * p.ldc + n);
+        } else if (ep.pos) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = min(row_base + i * 4 + sub, p.M - 1);
+            const int64_t pr = ep.pos_idx ? ep.pos_idx[r] : (int64_t)(r % ep.pos_rows);
+            add[i] = ld_f4(ep.pos + pr * (int64_t)p.N + n);
+          }
+        }
+        if (ep.accumulate) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 t = ld_f4(reinterpret_cast<const float*>(p.C) + (int64_t)max(prow[i], 0) * p.ldc + n);
+            if (two) add2[i] = t; else add[i] = t;
+          }
+        }
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t dst = stg + lane * 128 + ((j ^ (lane & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(raw[4 * j]), "r"(raw[4 * j + 1]),
+                     "r"(raw[4 * j + 2]), "r"(raw[4 * j + 3]) : "memory");
+      }
+      if (c + 32 < c_hi) {
+        tmem_ld32_issue(taddr + c + 32, raw);      // next block is in flight while this one is stored
+      } else {
+        release();                                  // accumulator drained: the MMA warp may reuse it
+      }
+      __syncwarp();
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rl = i * 4 + sub;
+        v[i] = lds_f4(stg + rl * 128 + ((c4 ^ (rl & 7)) << 4));
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (prow[i] < 0) continue;
+        float* out = reinterpret_cast<float*>(p.C) + (int64_t)prow[i] * p.ldc + n;
+        if (p.split_k > 1) {
+          atomicAdd(reinterpret_cast<float4*>(out), v[i]);
+        } else {
+          f4_add(v[i], b4);
+          f4_add(v[i], add[i]);
+          if (two) f4_add(v[i], add2[i]);
+          *reinterpret_cast<float4*>(out) = v[i];
+        }
+      }
+    }
+  }
 }
 
 template <int EPI>
@@ -263,220 +454,15 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int cols_half = p.block_n / 2;
     const int c_lo = half * cols_half, c_hi = c_lo + cols_half;
     const uint32_t stg = epi_stage + ew * UG_EPI_STAGE_BYTES;
-    const int sub = lane >> 3, c4 = lane & 7;        // transposed phase: row i*4+sub, float4 column c4
-    const avj_epilogue& ep = p.ep;
-    // Everything the epilogue ADDS comes from HBM (fp32 residual stream, previous C of a `C +=`, the saved
-    // pre-activation of GELU').  The rows of the NEXT tile are pulled into L2 with bulk prefetches while
-    // this tile's MMAs are still running, so those loads do not pay a DRAM round trip mid-epilogue.
-    const bool want_pf = p.l2_prefetch && ((EPI == EPI_DACT) || ((EPI == EPI_TRANSPOSED || EPI == EPI_GENERIC) &&
-                         ((ep.residual != nullptr) || (ep.dact_aux != nullptr) || (ep.accumulate && p.split_k == 1))));
-    auto prefetch_tile = [&](int u) {
-      const int tile = u / p.split_k;
-      const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
-      const int r = m_blk * UG_BM + q * 32 + lane;
-      if (r >= p.M) return;
-      const int n0 = n_blk * p.block_n + c_lo;
-      const int64_t off = map_row(ep.out_map, r) * (int64_t)p.ldc + n0;
-      if (ep.residual) l2_prefetch(ep.residual + off, cols_half * 4);
-      if (ep.accumulate && p.split_k == 1) l2_prefetch(reinterpret_cast<const float*>(p.C) + off, cols_half * 4);
-      if (ep.dact_aux) l2_prefetch(reinterpret_cast<const bf16*>(ep.dact_aux) + (int64_t)r * p.N + n0, cols_half * 2);
-    };
-    if (want_pf && (int)blockIdx.x < n_units) prefetch_tile(blockIdx.x);
     uint32_t acc = 0, acc_phase = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
       const int tile = u / p.split_k;
       const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
       const int row_base = m_blk * UG_BM + q * 32;
-      if (want_pf && u + (int)gridDim.x < n_units) prefetch_tile(u + gridDim.x);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * UG_MAX_BN;
-      uint32_t raw[32];
-
-      if (EPI == EPI_PLAIN || EPI == EPI_GELU || EPI == EPI_DACT) {
-        // ---------------- direct: thread == row, 32 consecutive columns per step ----------------
-        // the warp's bias segment goes to shared memory once per tile (broadcast reads afterwards)
-        const bool has_bias = (EPI != EPI_DACT) && ep.bias != nullptr;
-        if (has_bias) {
-          __syncwarp();                               // every lane is done with the previous tile's bias
-          if (lane * 4 < cols_half) sts_f4(stg + lane * 16, ld_f4(ep.bias + n_blk * p.block_n + c_lo + lane * 4));
-          __syncwarp();
-        }
-        const int64_t row = row_base + lane;
-        const bool row_ok = row < p.M;
-        const int64_t prow = row_ok ? map_row(ep.out_map, row) : 0;
-        mbar_wait(tfull_bar + 8 * acc, acc_phase);
-        tc_fence_after();
-        tmem_ld32_issue(taddr + c_lo, raw);
-        for (int c = c_lo; c < c_hi; c += 32) {
-          const int n0 = n_blk * p.block_n + c;
-          uint4 aux[4];
-          if (EPI == EPI_DACT) {
-            const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.dact_aux) + row * (int64_t)p.N + n0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) aux[j] = row_ok ? ap[j] : make_uint4(0u, 0u, 0u, 0u);
-          }
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-          if (c + 32 < c_hi) {
-            tmem_ld32_issue(taddr + c + 32, raw);
-          } else {
-            tc_fence_before();
-            mbar_arrive(tempty_bar + 8 * acc);
-          }
-          if (has_bias) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = lds_f4(stg + (c - c_lo + j * 4) * 4);
-              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-            }
-          }
-          if (!row_ok) continue;
-          if (EPI == EPI_GELU) {
-            if (ep.pre_out) {
-              uint4* pp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.pre_out) + row * (int64_t)p.N + n0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                pp[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                   pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-            }
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_fwd<true>(v[i]);
-          }
-          if (EPI == EPI_DACT) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t w[4] = {aux[j].x, aux[j].y, aux[j].z, aux[j].w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float x0, x1;
-                unpack_bf16x2(w[e], x0, x1);
-                v[8 * j + 2 * e] *= gelu_bwd<true>(x0);
-                v[8 * j + 2 * e + 1] *= gelu_bwd<true>(x1);
-              }
-            }
-          }
-          if (ep.out_dtype == AVJ_F32) {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + prow * (int64_t)p.ldc + n0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.C) + prow * (int64_t)p.ldc + n0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              op[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                 pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-          }
-        }
-      } else if (EPI == EPI_GENERIC) {
-        // ---------------- generic direct path: every epilogue field evaluated at run time ----------------
-        mbar_wait(tfull_bar + 8 * acc, acc_phase);
-        tc_fence_after();
-        tmem_ld32_issue(taddr + c_lo, raw);
-        const int64_t row = row_base + lane;
-        const bool row_ok = row < p.M;
-        for (int c = c_lo; c < c_hi; c += 32) {
-          const int n0 = n_blk * p.block_n + c;
-          float add[32];
-          if (p.split_k == 1 && row_ok) epilogue_prefetch<32>(ep, p.C, p.ldc, p.N, row, n0, add);
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-          if (c + 32 < c_hi) {
-            tmem_ld32_issue(taddr + c + 32, raw);
-          } else {
-            tc_fence_before();
-            mbar_arrive(tempty_bar + 8 * acc);
-          }
-          if (row_ok) {
-            if (p.split_k > 1) {
-              float* out = reinterpret_cast<float*>(p.C) + map_row(ep.out_map, row) * (int64_t)p.ldc + n0;
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) atomicAdd(reinterpret_cast<float4*>(out + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
-            } else {
-              epilogue_apply_store<bf16, 32, true>(ep, p.C, p.ldc, p.N, row, n0, v, add);
-            }
-          }
-        }
-      } else {
-        // ---------------- transposed: coalesced 4 rows x 128 B per warp instruction, fp32 C ----------------
-        int prow[8];                                   // physical C row of my 8 rows, -1 = past M
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = row_base + i * 4 + sub;
-          prow[i] = r < p.M ? (int)map_row(ep.out_map, r) : -1;
-        }
-        mbar_wait(tfull_bar + 8 * acc, acc_phase);
-        tc_fence_after();
-        tmem_ld32_issue(taddr + c_lo, raw);
-        for (int c = c_lo; c < c_hi; c += 32) {
-          const int n = n_blk * p.block_n + c + c4 * 4;
-          // ---- addends that do not depend on the accumulator: ALL loads are issued back to back (rows past
-          // M are clamped to a valid row and discarded) so one chunk costs one memory round trip, and they
-          // are in flight while the TMEM load completes
-          float4 add[8], add2[8];
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          const bool two = ep.accumulate && (ep.residual || ep.pos);
-          if (p.split_k == 1) {
-            if (ep.bias) b4 = ld_f4(ep.bias + n);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { add[i] = make_float4(0.f, 0.f, 0.f, 0.f); add2[i] = add[i]; }
-            if (ep.residual) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) add[i] = ld_f4(ep.residual + (int64_t)max(prow[i], 0) * p.ldc + n);
-            } else if (ep.pos) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int r = min(row_base + i * 4 + sub, p.M - 1);
-                const int64_t pr = ep.pos_idx ? ep.pos_idx[r] : (int64_t)(r % ep.pos_rows);
-                add[i] = ld_f4(ep.pos + pr * (int64_t)p.N + n);
-              }
-            }
-            if (ep.accumulate) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 t = ld_f4(reinterpret_cast<const float*>(p.C) + (int64_t)max(prow[i], 0) * p.ldc + n);
-                if (two) add2[i] = t; else add[i] = t;
-              }
-            }
-          }
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t dst = stg + lane * 128 + ((j ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(raw[4 * j]), "r"(raw[4 * j + 1]),
-                         "r"(raw[4 * j + 2]), "r"(raw[4 * j + 3]) : "memory");
-          }
-          if (c + 32 < c_hi) {
-            tmem_ld32_issue(taddr + c + 32, raw);      // next block is in flight while this one is stored
-          } else {
-            tc_fence_before();
-            mbar_arrive(tempty_bar + 8 * acc);         // accumulator drained: the MMA warp may reuse it
-          }
-          __syncwarp();
-          float4 v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rl = i * 4 + sub;
-            v[i] = lds_f4(stg + rl * 128 + ((c4 ^ (rl & 7)) << 4));
-          }
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (prow[i] < 0) continue;
-            float* out = reinterpret_cast<float*>(p.C) + (int64_t)prow[i] * p.ldc + n;
-            if (p.split_k > 1) {
-              atomicAdd(reinterpret_cast<float4*>(out), v[i]);
-            } else {
-              f4_add(v[i], b4);
-              f4_add(v[i], add[i]);
-              if (two) f4_add(v[i], add2[i]);
-              *reinterpret_cast<float4*>(out) = v[i];
-            }
-          }
-        }
-      }
+      epilogue_tile<EPI>(p, row_base, n_blk, taddr, stg, lane, c_lo, c_hi,
+                         [&] { mbar_wait(tfull_bar + 8 * acc, acc_phase); tc_fence_after(); },
+                         [&] { tc_fence_before(); mbar_arrive(tempty_bar + 8 * acc); });
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -486,6 +472,204 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 2-CTA kernel: one 256 x BN output tile per CTA PAIR (tcgen05.mma.cta_group::2)
+// ------------------------------------------------------------------------------------------
+// The two CTAs of a cluster sit on the two SMs of a TPC.  Each loads ITS 128 rows of A and ITS half of the
+// B tile (BN/2 rows or columns); the leader's single MMA thread issues M = 256 instructions that read both
+// CTAs' shared memory and write both CTAs' TMEM.  Per SM that is 8 KB instead of 12 KB of operand traffic
+// per 128x256x16 MACs -- shared-memory bandwidth (TMA writes + MMA reads) is what caps the 1-CTA kernel at
+// ~77 % of the tensor pipe -- and the smaller stages make room for a 6-deep ring.
+//   TMA      : both CTAs, every load completes on the LEADER's full barrier (expect_tx covers both halves)
+//   MMA      : leader only; tcgen05.commit multicasts to both CTAs' empty / tmem-full barriers
+//   epilogue : both CTAs on their own 128 accumulator rows; one lane per warp arrives (remotely for the
+//              peer) on the leader's tmem-empty barrier
+#define UG2_STAGES 6
+#define UG2_STAGE_BYTES (UG_BM * UG_BK * 2)                       // 16 KB for A and 16 KB for the B half
+#define UG2_SMEM_BYTES (UG2_STAGES * 2 * UG2_STAGE_BYTES + 1024 + 256 + UG_EPI_WARPS * UG_EPI_STAGE_BYTES)
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UG_THREADS, 1)
+gemm_umma2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const UmmaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t smem_a = base;
+  const uint32_t smem_b = base + UG2_STAGES * UG2_STAGE_BYTES;
+  const uint32_t bars = smem_b + UG2_STAGES * UG2_STAGE_BYTES;
+  const uint32_t full_bar = bars;                       // [UG2_STAGES]  (used in the leader only)
+  const uint32_t empty_bar = bars + 8 * UG2_STAGES;     // [UG2_STAGES]
+  const uint32_t tfull_bar = bars + 16 * UG2_STAGES;    // [2]
+  const uint32_t tempty_bar = tfull_bar + 16;           // [2]           (used in the leader only)
+  const uint32_t tmem_slot = tempty_bar + 16;           // u32
+  const uint32_t epi_stage = bars + 256;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
+    for (int i = 0; i < UG2_STAGES; ++i) { mbar_init(full_bar + 8 * i, 1); mbar_init(empty_bar + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + 8 * i, 1); mbar_init(tempty_bar + 8 * i, 2 * UG_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();                                   // barrier inits + TMEM allocation visible pair-wide
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int n_units = p.tiles_m * p.tiles_n * p.split_k;   // tiles_m counts 256-row tiles here
+  const int half_n = p.block_n / 2;
+
+  if (warp < 4) {
+    reg_dec<40>();
+    if (warp == 0) {
+      // ================= TMA producer (both CTAs) =================
+      if (lane == 0) {
+        const uint32_t stage_tx = 2u * (UG2_STAGE_BYTES + (uint32_t)half_n * UG_BK * 2);   // both CTAs' bytes
+        uint32_t stage = 0, phase = 0;
+        for (int u = cluster_id; u < n_units; u += n_clusters) {
+          const int tile = u / p.split_k, ks = u % p.split_k;
+          const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+          const int m0 = m_blk * 2 * UG_BM + (int)rank * UG_BM;           // my 128 rows of the 256-row tile
+          const int n0 = n_blk * p.block_n + (int)rank * half_n;          // my half of the B tile
+          const int kb0 = ks * p.kb_per_split;
+          const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+            const uint32_t fb = mapa_u32(full_bar + 8 * stage, 0);        // the leader's barrier
+            if (leader) mbar_expect_tx(full_bar + 8 * stage, stage_tx);
+            const uint32_t sa = smem_a + stage * UG2_STAGE_BYTES;
+            const uint32_t sb = smem_b + stage * UG2_STAGE_BYTES;
+            if (!p.a_mn_major) {
+              tma_load_2d_2sm(sa, &tma_a, fb, kb * UG_BK, m0);
+            } else {
+              tma_load_2d_2sm(sa, &tma_a, fb, m0, kb * UG_BK);
+              tma_load_2d_2sm(sa + 8192, &tma_a, fb, m0 + 64, kb * UG_BK);
+            }
+            if (!p.b_mn_major) {
+              tma_load_2d_2sm(sb, &tma_b, fb, kb * UG_BK, n0);
+            } else {
+              for (int j = 0; j < half_n / 64; ++j)
+                tma_load_2d_2sm(sb + j * 8192, &tma_b, fb, n0 + j * 64, kb * UG_BK);
+            }
+            if (++stage == UG2_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if (warp == 1 && leader) {
+      // ================= MMA issuer (leader CTA only) =================
+      if (lane == 0) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn_major << 15) |
+                               ((uint32_t)p.b_mn_major << 16) | ((uint32_t)(p.block_n >> 3) << 17) |
+                               ((uint32_t)((2 * UG_BM) >> 4) << 24);
+        uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+        for (int u = cluster_id; u < n_units; u += n_clusters) {
+          const int ks = u % p.split_k;
+          const int kb0 = ks * p.kb_per_split;
+          const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+          mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * UG_MAX_BN;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(full_bar + 8 * stage, phase);
+            tc_fence_after();
+            const uint32_t sa = smem_a + stage * UG2_STAGE_BYTES;
+            const uint32_t sb = smem_b + stage * UG2_STAGE_BYTES;
+            const uint64_t adesc0 = p.a_mn_major ? make_desc(sa, p.mn_lbo, p.mn_sbo) : make_desc(sa, 1, 64);
+            const uint64_t bdesc0 = p.b_mn_major ? make_desc(sb, p.mn_lbo, p.mn_sbo) : make_desc(sb, 1, 64);
+            const uint32_t a_adv = p.a_mn_major ? p.mn_kadv : 2u;
+            const uint32_t b_adv = p.b_mn_major ? p.mn_kadv : 2u;
+#pragma unroll
+            for (int k = 0; k < UG_BK / 16; ++k) {
+              tc_mma_bf16_2sm(tmem_d, adesc0 + (uint64_t)(k * a_adv), bdesc0 + (uint64_t)(k * b_adv), idesc,
+                              (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            tc_commit_2sm(empty_bar + 8 * stage);        // frees this stage in BOTH CTAs
+            if (++stage == UG2_STAGES) { stage = 0; phase ^= 1; }
+          }
+          tc_commit_2sm(tfull_bar + 8 * acc);            // accumulator complete -> both epilogues
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ================= epilogue warpgroups (both CTAs, own 128 accumulator rows) =================
+    reg_inc<232>();
+    const int q = warp & 3;
+    const int ew = warp - 4;
+    const int half = ew >> 2;
+    const int cols_half = p.block_n / 2;
+    const int c_lo = half * cols_half, c_hi = c_lo + cols_half;
+    const uint32_t stg = epi_stage + ew * UG_EPI_STAGE_BYTES;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int u = cluster_id; u < n_units; u += n_clusters) {
+      const int tile = u / p.split_k;
+      const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+      const int row_base = m_blk * 2 * UG_BM + (int)rank * UG_BM + q * 32;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * UG_MAX_BN;
+      const uint32_t leader_tempty = mapa_u32(tempty_bar + 8 * acc, 0);
+      epilogue_tile<EPI>(p, row_base, n_blk, taddr, stg, lane, c_lo, c_hi,
+                         [&] { mbar_wait(tfull_bar + 8 * acc, acc_phase); tc_fence_after(); },
+                         [&] { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive_cluster(leader_tempty); });
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                                   // the peer's smem / barriers / TMEM stay alive until both are done
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -582,9 +766,6 @@ int avj_gemm_umma(int layout, const void* A, const void* B, void* C, int M, int 
   UmmaParams p;
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.C = C; p.ep = ep;
-  p.block_n = pick_block_n(N);
-  p.tiles_m = (M + UG_BM - 1) / UG_BM;
-  p.tiles_n = N / p.block_n;
   p.k_blocks = (K + UG_BK - 1) / UG_BK;
   p.a_mn_major = (layout == AVJ_GEMM_TN);
   p.b_mn_major = (layout != AVJ_GEMM_NT);
@@ -595,13 +776,29 @@ int avj_gemm_umma(int layout, const void* A, const void* B, void* C, int M, int 
   static const uint32_t mn_kadv = env_u32("AVJ_UMMA_MN_KADV", 2048 / 16);
   p.mn_lbo = mn_lbo; p.mn_sbo = mn_sbo; p.mn_kadv = mn_kadv;
 
+  // ---- 1-CTA (128 x BN tiles) or CTA-pair (256 x BN tiles, cta_group::2) kernel
+  //   AVJ_GEMM_2CTA = 0 never | 1 whenever legal | 2 (default) when the problem has at least 256 rows
+  static const uint32_t mode2 = env_u32("AVJ_GEMM_2CTA", 2);
+  p.block_n = pick_block_n(N);
+  bool two = mode2 != 0 && (mode2 == 1 || M >= 2 * UG_BM);
+  if (two && p.b_mn_major) {
+    // each CTA loads BN/2 columns of an MN-major B tile as whole 64-column TMA boxes
+    if (N % 256 == 0) p.block_n = 256;
+    else if (N % 128 == 0) p.block_n = 128;
+    else two = false;
+  }
+  const int tile_m = two ? 2 * UG_BM : UG_BM;
+  p.tiles_m = (M + tile_m - 1) / tile_m;
+  p.tiles_n = N / p.block_n;
+
   const int sms = avj_num_sms();
+  const int workers = two ? sms / 2 : sms;               // CTAs or CTA pairs
   const int tiles = p.tiles_m * p.tiles_n;
   p.split_k = 1;
   const bool pure_accumulate = ep.accumulate && ep.out_dtype == AVJ_F32 && !ep.bias && !ep.residual && !ep.pos &&
                                !ep.act && !ep.dact_aux;
-  if (pure_accumulate && tiles < 2 * sms && p.k_blocks >= 8) {
-    int want = (2 * sms + tiles - 1) / tiles;
+  if (pure_accumulate && tiles < 2 * workers && p.k_blocks >= 8) {
+    int want = (2 * workers + tiles - 1) / tiles;
     int max_split = p.k_blocks / 4;
     if (want > max_split) want = max_split;
     if (want < 1) want = 1;
@@ -615,12 +812,11 @@ int avj_gemm_umma(int layout, const void* A, const void* B, void* C, int M, int 
   if (!p.a_mn_major) rc = get_tensor_map(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, UG_BK, UG_BM, &ma);
   else               rc = get_tensor_map(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, UG_BK, &ma);
   if (rc) return rc;
-  if (!p.b_mn_major) rc = get_tensor_map(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, UG_BK, (uint32_t)p.block_n, &mb);
+  const uint32_t b_rows = (uint32_t)(two ? p.block_n / 2 : p.block_n);   // K-major B box: rows of W per CTA
+  if (!p.b_mn_major) rc = get_tensor_map(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, UG_BK, b_rows, &mb);
   else               rc = get_tensor_map(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, UG_BK, &mb);
   if (rc) return rc;
 
-  static const uint32_t l2pf = env_u32("AVJ_GEMM_L2PF", 0);
-  p.l2_prefetch = (int)l2pf;
   // ---- epilogue specialisation
   const bool adds = ep.residual || ep.pos || ep.accumulate;
   int epi;
@@ -633,19 +829,28 @@ int avj_gemm_umma(int layout, const void* A, const void* B, void* C, int M, int 
   else epi = EPI_PLAIN;
 
   typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const UmmaParams);
-  static const kern_t kerns[5] = {gemm_umma_kernel<EPI_PLAIN>, gemm_umma_kernel<EPI_GELU>, gemm_umma_kernel<EPI_DACT>,
-                                  gemm_umma_kernel<EPI_TRANSPOSED>, gemm_umma_kernel<EPI_GENERIC>};
+  static const kern_t kerns[10] = {
+      gemm_umma_kernel<EPI_PLAIN>, gemm_umma_kernel<EPI_GELU>, gemm_umma_kernel<EPI_DACT>,
+      gemm_umma_kernel<EPI_TRANSPOSED>, gemm_umma_kernel<EPI_GENERIC>,
+      gemm_umma2_kernel<EPI_PLAIN>, gemm_umma2_kernel<EPI_GELU>, gemm_umma2_kernel<EPI_DACT>,
+      gemm_umma2_kernel<EPI_TRANSPOSED>, gemm_umma2_kernel<EPI_GENERIC>};
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    for (int i = 0; i < 5 && attr_err == cudaSuccess; ++i)
-      attr_err = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, UG_SMEM_BYTES);
+    for (int i = 0; i < 10 && attr_err == cudaSuccess; ++i)
+      attr_err = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      i < 5 ? UG_SMEM_BYTES : UG2_SMEM_BYTES);
   });
   AVJ_CHECK(attr_err == cudaSuccess, "cudaFuncSetAttribute(gemm_umma_kernel) failed: %s", cudaGetErrorString(attr_err));
 
   const int units = tiles * p.split_k;
-  const int grid = units < sms ? units : sms;
-  kerns[epi]<<<grid, UG_THREADS, UG_SMEM_BYTES, s>>>(ma, mb, p);
+  if (two) {
+    const int clusters = units < workers ? units : workers;
+    kerns[5 + epi]<<<2 * clusters, UG_THREADS, UG2_SMEM_BYTES, s>>>(ma, mb, p);
+  } else {
+    const int grid = units < sms ? units : sms;
+    kerns[epi]<<<grid, UG_THREADS, UG_SMEM_BYTES, s>>>(ma, mb, p);
+  }
   AVJ_LAUNCH_CHECK();
   return 0;
 }

@@ -253,15 +253,19 @@ def main():
         dev_masks = [to_device(host_masks[first_set + i]) for i in range(K + W)] if not e2e else None
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches = 0
+        if e2e:
+            # public-API path: every step's clips, spectrograms and masks start in PINNED HOST memory and are
+            # staged by the package's DevicePrefetcher (copy stream, one batch ahead); the loss is read back
+            # to the host every step (sync=True -> float(loss)).
+            from avjepa_b200.app.avjepa.prefetch import DevicePrefetcher
+            feed = DevicePrefetcher(((host_clips, host_asgram, host_masks[first_set + i]) for i in range(K + W)), dev)
         for i in range(K + W):
             if i == W:
                 barrier()
                 launches = _cabi.launch_count
                 ev0.record()
             if e2e:
-                c = host_clips.to(dev, non_blocking=True)
-                a = host_asgram.to(dev, non_blocking=True)
-                m = to_device(host_masks[first_set + i])
+                c, a, m = next(feed)
                 out = step(c, a, *m, epoch=0, sync=True)          # float(loss): D2H read every step
             else:
                 out = step(clips_d, asgram_d, *dev_masks[i], epoch=0, sync=False)

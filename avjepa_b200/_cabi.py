@@ -87,7 +87,8 @@ PROTOTYPES = {
     'avj_colsum': (_i, [_vp, _i, _i, RowMap, _vp, _i, _i, _vp, _vp]),
     'avj_layernorm_fwd': (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _f, _vp]),
     'avj_layernorm_bwd_ws_floats': (_i64, [_i, _i]),
-    'avj_layernorm_bwd': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
+    'avj_layernorm_bwd': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    'avj_colsum2': (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp]),
     'avj_attention_fwd': (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     'avj_attention_bwd_ws_floats': (_i64, [_i, _i, _i, _i]),
     'avj_attention_bwd': (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),

@@ -297,6 +297,86 @@ extern "C" int avj_colsum(const void* in, int in_dtype, int ld, avj_rowmap map, 
   return 0;
 }
 
+// Two column sums over the same rows in one launch: blockIdx.x < gx1 serves (in1, D1), the rest (in2, D2).
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum2_partial_kernel(const T* __restrict__ in1, int ld1, int D1, const T* __restrict__ in2, int ld2, int D2,
+                       float* __restrict__ ws, int rows, int chunk, int gx1) {
+  __shared__ float sm[8][32][8 + 1];
+  const bool second = (int)blockIdx.x >= gx1;
+  const T* in = second ? in2 : in1;
+  const int ld = second ? ld2 : ld1, D = second ? D2 : D1;
+  const int c0 = (((int)blockIdx.x - (second ? gx1 : 0)) * 32 + threadIdx.x) * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c0 < D) {
+    const int r_beg = blockIdx.y * chunk, r_end = min(rows, r_beg + chunk);
+    int r = r_beg + threadIdx.y;
+    for (; r + 24 < r_end; r += 32) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load8<T>(in + (int64_t)(r + 8 * u) * ld + c0, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[u][j];
+    }
+    for (; r < r_end; r += 8) {
+      float v[8];
+      load8<T>(in + (int64_t)r * ld + c0, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[threadIdx.y][threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (threadIdx.y == 0 && c0 < D) {
+    float* w = ws + (int64_t)blockIdx.y * (D1 + D2) + (second ? D1 : 0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) s += sm[y][threadIdx.x][j];
+      w[c0 + j] = s;
+    }
+  }
+}
+
+__global__ void colsum2_final_kernel(const float* __restrict__ ws, float* __restrict__ out1, float* __restrict__ out2,
+                                     int ny, int D1, int D2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D1 + D2) return;
+  float s = 0.f;
+#pragma unroll 8
+  for (int i = 0; i < ny; ++i) s += ws[(int64_t)i * (D1 + D2) + c];
+  if (c < D1) out1[c] += s; else out2[c - D1] += s;
+}
+
+extern "C" int avj_colsum2(const void* in1, int ld1, int D1, float* out1, const void* in2, int ld2, int D2, float* out2,
+                           int in_dtype, int rows, float* ws, void* stream) {
+  AVJ_CHECK(D1 % 8 == 0 && ld1 % 8 == 0 && D2 % 8 == 0 && ld2 % 8 == 0, "avj_colsum2: D/ld must be multiples of 8");
+  AVJ_CHECK(out1 && out2 && ws, "avj_colsum2: NULL output/workspace");
+  if (rows == 0) return 0;
+  AvjProfScope prof(AVJ_FAM_COLSUM, (double)rows * (D1 + D2) * (in_dtype == AVJ_BF16 ? 2 : 4), stream);
+  const int gx1 = (D1 + 255) / 256, gx = gx1 + (D2 + 255) / 256;
+  int ny = (4 * avj_num_sms() + gx - 1) / gx;
+  if (ny > COLSUM_MAX_Y) ny = COLSUM_MAX_Y;
+  if (ny > (rows + 63) / 64) ny = (rows + 63) / 64;
+  if (ny < 1) ny = 1;
+  int chunk = (rows + ny - 1) / ny;
+  chunk = (chunk + 7) / 8 * 8;
+  ny = (rows + chunk - 1) / chunk;
+  dim3 grid(gx, ny), block(32, 8);
+  if (in_dtype == AVJ_BF16)
+    colsum2_partial_kernel<bf16><<<grid, block, 0, as_stream(stream)>>>((const bf16*)in1, ld1, D1, (const bf16*)in2, ld2, D2, ws, rows, chunk, gx1);
+  else
+    colsum2_partial_kernel<float><<<grid, block, 0, as_stream(stream)>>>((const float*)in1, ld1, D1, (const float*)in2, ld2, D2, ws, rows, chunk, gx1);
+  AVJ_LAUNCH_CHECK();
+  colsum2_final_kernel<<<(D1 + D2 + 63) / 64, 64, 0, as_stream(stream)>>>(ws, out1, out2, ny, D1, D2);
+  AVJ_LAUNCH_CHECK();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // K10 loss forward+backward in one pass, deterministic two-stage reduction.
 // ------------------------------------------------------------------------------------------

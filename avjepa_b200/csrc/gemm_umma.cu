@@ -336,8 +336,11 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int row_base,
   }
 }
 
-template <int EPI>
-__global__ void __launch_bounds__(UG_THREADS, 1)
+// EW = number of epilogue warps: 8 (two per TMEM lane quarter, half of the columns each) or 16 (four per
+// quarter, a quarter of the columns each) for the thread==row epilogues, which are latency- rather than
+// issue-bound and double their throughput with twice the warps in flight.
+template <int EPI, int EW>
+__global__ void __launch_bounds__(128 + 32 * EW, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const UmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -359,7 +362,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
     for (int i = 0; i < UG_STAGES; ++i) { mbar_init(full_bar + 8 * i, 1); mbar_init(empty_bar + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + 8 * i, 1); mbar_init(tempty_bar + 8 * i, 32 * UG_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + 8 * i, 1); mbar_init(tempty_bar + 8 * i, 32 * EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -445,15 +448,15 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
     }
   } else {
-    // ================= epilogue warpgroups (8 warps, 232 registers each) =================
-    // Two warps per TMEM lane quarter, each taking half of the tile's columns, 32 columns at a time.
-    reg_inc<232>();
+    // ================= epilogue warpgroups (EW warps) =================
+    // EW/4 warps per TMEM lane quarter, each taking BN/(EW/4) of the tile's columns, 32 columns at a time.
+    reg_inc<EW == 8 ? 232 : 112>();
     const int q = warp & 3;                          // TMEM lane quarter this warp may touch
     const int ew = warp - 4;
-    const int half = ew >> 2;
-    const int cols_half = p.block_n / 2;
-    const int c_lo = half * cols_half, c_hi = c_lo + cols_half;
-    const uint32_t stg = epi_stage + ew * UG_EPI_STAGE_BYTES;
+    const int part = ew >> 2;
+    const int cols_part = p.block_n / (EW / 4);
+    const int c_lo = part * cols_part, c_hi = c_lo + cols_part;
+    const uint32_t stg = epi_stage + ew * (UG_EPI_WARPS * UG_EPI_STAGE_BYTES / EW);
     uint32_t acc = 0, acc_phase = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
       const int tile = u / p.split_k;
@@ -529,8 +532,8 @@ __device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
-template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UG_THREADS, 1)
+template <int EPI, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
 gemm_umma2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const UmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -555,7 +558,7 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
     for (int i = 0; i < UG2_STAGES; ++i) { mbar_init(full_bar + 8 * i, 1); mbar_init(empty_bar + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + 8 * i, 1); mbar_init(tempty_bar + 8 * i, 2 * UG_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + 8 * i, 1); mbar_init(tempty_bar + 8 * i, 2 * EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -644,13 +647,13 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     }
   } else {
     // ================= epilogue warpgroups (both CTAs, own 128 accumulator rows) =================
-    reg_inc<232>();
+    reg_inc<EW == 8 ? 232 : 112>();
     const int q = warp & 3;
     const int ew = warp - 4;
-    const int half = ew >> 2;
-    const int cols_half = p.block_n / 2;
-    const int c_lo = half * cols_half, c_hi = c_lo + cols_half;
-    const uint32_t stg = epi_stage + ew * UG_EPI_STAGE_BYTES;
+    const int part = ew >> 2;
+    const int cols_part = p.block_n / (EW / 4);
+    const int c_lo = part * cols_part, c_hi = c_lo + cols_part;
+    const uint32_t stg = epi_stage + ew * (UG_EPI_WARPS * UG_EPI_STAGE_BYTES / EW);
     uint32_t acc = 0, acc_phase = 0;
     for (int u = cluster_id; u < n_units; u += n_clusters) {
       const int tile = u / p.split_k;
@@ -828,28 +831,39 @@ int avj_gemm_umma(int layout, const void* A, const void* B, void* C, int M, int 
   else if (ep.dact_aux) epi = EPI_DACT;
   else epi = EPI_PLAIN;
 
+  // thread==row epilogues run 16 epilogue warps when the tile splits into four 32-column-aligned parts
+  static const uint32_t ew16 = env_u32("AVJ_GEMM_EW16", 1);
+  const bool wide = ew16 && epi <= EPI_DACT && p.block_n % 128 == 0;
+
   typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const UmmaParams);
-  static const kern_t kerns[10] = {
-      gemm_umma_kernel<EPI_PLAIN>, gemm_umma_kernel<EPI_GELU>, gemm_umma_kernel<EPI_DACT>,
-      gemm_umma_kernel<EPI_TRANSPOSED>, gemm_umma_kernel<EPI_GENERIC>,
-      gemm_umma2_kernel<EPI_PLAIN>, gemm_umma2_kernel<EPI_GELU>, gemm_umma2_kernel<EPI_DACT>,
-      gemm_umma2_kernel<EPI_TRANSPOSED>, gemm_umma2_kernel<EPI_GENERIC>};
+  // [two][wide][epi]
+  static const kern_t kerns[2][2][5] = {
+      {{gemm_umma_kernel<EPI_PLAIN, 8>, gemm_umma_kernel<EPI_GELU, 8>, gemm_umma_kernel<EPI_DACT, 8>,
+        gemm_umma_kernel<EPI_TRANSPOSED, 8>, gemm_umma_kernel<EPI_GENERIC, 8>},
+       {gemm_umma_kernel<EPI_PLAIN, 16>, gemm_umma_kernel<EPI_GELU, 16>, gemm_umma_kernel<EPI_DACT, 16>, nullptr, nullptr}},
+      {{gemm_umma2_kernel<EPI_PLAIN, 8>, gemm_umma2_kernel<EPI_GELU, 8>, gemm_umma2_kernel<EPI_DACT, 8>,
+        gemm_umma2_kernel<EPI_TRANSPOSED, 8>, gemm_umma2_kernel<EPI_GENERIC, 8>},
+       {gemm_umma2_kernel<EPI_PLAIN, 16>, gemm_umma2_kernel<EPI_GELU, 16>, gemm_umma2_kernel<EPI_DACT, 16>, nullptr, nullptr}}};
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    for (int i = 0; i < 10 && attr_err == cudaSuccess; ++i)
-      attr_err = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      i < 5 ? UG_SMEM_BYTES : UG2_SMEM_BYTES);
+    for (int t = 0; t < 2; ++t)
+      for (int w = 0; w < 2; ++w)
+        for (int i = 0; i < 5 && attr_err == cudaSuccess; ++i)
+          if (kerns[t][w][i])
+            attr_err = cudaFuncSetAttribute(kerns[t][w][i], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            t == 0 ? UG_SMEM_BYTES : UG2_SMEM_BYTES);
   });
   AVJ_CHECK(attr_err == cudaSuccess, "cudaFuncSetAttribute(gemm_umma_kernel) failed: %s", cudaGetErrorString(attr_err));
 
   const int units = tiles * p.split_k;
+  const int threads = 128 + 32 * (wide ? 16 : 8);
   if (two) {
     const int clusters = units < workers ? units : workers;
-    kerns[5 + epi]<<<2 * clusters, UG_THREADS, UG2_SMEM_BYTES, s>>>(ma, mb, p);
+    kerns[1][wide][epi]<<<2 * clusters, threads, UG2_SMEM_BYTES, s>>>(ma, mb, p);
   } else {
     const int grid = units < sms ? units : sms;
-    kerns[epi]<<<grid, UG_THREADS, UG_SMEM_BYTES, s>>>(ma, mb, p);
+    kerns[0][wide][epi]<<<grid, threads, UG_SMEM_BYTES, s>>>(ma, mb, p);
   }
   AVJ_LAUNCH_CHECK();
   return 0;

@@ -94,7 +94,7 @@ extern "C" int avj_layernorm_fwd(const float* x, const float* gamma, const float
 // ------------------------------------------------------------------------------------------
 extern "C" int64_t avj_layernorm_bwd_ws_floats(int rows, int D) {
   (void)rows;
-  return (int64_t)LN_MAX_BLOCKS * 2 * D;
+  return (int64_t)LN_MAX_BLOCKS * 3 * D;
 }
 
 template <typename TDY>
@@ -122,17 +122,20 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 2)
 layernorm_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
                      float* __restrict__ dx, TLP* __restrict__ dx_lp, float* __restrict__ ws, int want_dgamma,
-                     int rows, int D) {
-  extern __shared__ float sm[];   // [LN_WARPS][2][D] partials, only when want_dgamma
+                     int want_colsum, int rows, int D) {
+  extern __shared__ float sm[];   // [LN_WARPS][3][D] partials: d(gamma), d(beta), column sum of dx
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = D / 4;
-  float4* sg = reinterpret_cast<float4*>(sm + (size_t)warp * 2 * D);
+  float4* sg = reinterpret_cast<float4*>(sm + (size_t)warp * 3 * D);
   float4* sb = sg + nvec;
-  if (want_dgamma) {
+  float4* sc = sb + nvec;
+  if (want_dgamma || want_colsum) {
 #pragma unroll
     for (int i = 0; i < NV4; ++i) {
       const int c = lane + i * 32;
-      if (c < nvec) { sg[c] = make_float4(0.f, 0.f, 0.f, 0.f); sb[c] = make_float4(0.f, 0.f, 0.f, 0.f); }
+      if (c < nvec) {
+        sg[c] = make_float4(0.f, 0.f, 0.f, 0.f); sb[c] = make_float4(0.f, 0.f, 0.f, 0.f); sc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
   }
 
@@ -180,6 +183,11 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ x, co
         const float4 o = make_float4(dr[i].x + rs * (d[i].x - m1 - xv[i].x * m2), dr[i].y + rs * (d[i].y - m1 - xv[i].y * m2),
                                      dr[i].z + rs * (d[i].z - m1 - xv[i].z * m2), dr[i].w + rs * (d[i].w - m1 - xv[i].w * m2));
         reinterpret_cast<float4*>(dx + r * D)[c] = o;
+        if (want_colsum) {
+          float4 a = sc[c];
+          a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+          sc[c] = a;
+        }
         if (dx_lp) {
           if (sizeof(TLP) == 4) {
             reinterpret_cast<float4*>(dx_lp + r * D)[c] = o;
@@ -192,13 +200,13 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ x, co
     }
   }
 
-  if (want_dgamma) {
+  if (want_dgamma || want_colsum) {
     __syncthreads();
-    for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
+    for (int c = threadIdx.x; c < 3 * D; c += blockDim.x) {
       float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < LN_WARPS; ++w) t += sm[(size_t)w * 2 * D + c];
-      ws[(size_t)blockIdx.x * 2 * D + c] = t;
+      for (int w = 0; w < LN_WARPS; ++w) t += sm[(size_t)w * 3 * D + c];
+      ws[(size_t)blockIdx.x * 3 * D + c] = t;
     }
   }
 }
@@ -206,39 +214,41 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ x, co
 // cross-block reduction of the [nblocks][2D] partials: 32 columns x 8 row groups per block
 __global__ void __launch_bounds__(256)
 layernorm_bwd_final_kernel(const float* __restrict__ ws, int nblocks, int D,
-                           float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                           float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcolsum) {
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
   float t = 0.f;
-  if (c < 2 * D)
-    for (int b = ty; b < nblocks; b += 8) t += ws[(size_t)b * 2 * D + c];
+  if (c < 3 * D)
+    for (int b = ty; b < nblocks; b += 8) t += ws[(size_t)b * 3 * D + c];
   red[ty][tx] = t;
   __syncthreads();
-  if (ty == 0 && c < 2 * D) {
+  if (ty == 0 && c < 3 * D) {
     float v = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) v += red[j][tx];
     if (c < D) { if (dgamma) dgamma[c] += v; }
-    else { if (dbeta) dbeta[c - D] += v; }
+    else if (c < 2 * D) { if (dbeta) dbeta[c - D] += v; }
+    else { if (dcolsum) dcolsum[c - 2 * D] += v; }
   }
 }
 
 template <typename TDY, typename TLP>
 static int launch_ln_bwd(const TDY* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
-                         const float* dres, float* dx, TLP* dx_lp, float* dgamma, float* dbeta, float* ws,
+                         const float* dres, float* dx, TLP* dx_lp, float* dgamma, float* dbeta, float* dcolsum, float* ws,
                          int rows, int D, cudaStream_t s) {
   const int nv4 = (D / 4 + 31) / 32;
   int grid = (rows + LN_WARPS - 1) / LN_WARPS;
   if (grid > LN_MAX_BLOCKS) grid = LN_MAX_BLOCKS;
   const int want = (dgamma != nullptr || dbeta != nullptr) ? 1 : 0;
-  const size_t smem = want ? (size_t)LN_WARPS * 2 * D * sizeof(float) : 0;
+  const int want_cs = dcolsum != nullptr ? 1 : 0;
+  const size_t smem = (want || want_cs) ? (size_t)LN_WARPS * 3 * D * sizeof(float) : 0;
 #define LNB_CASE(NV)                                                                                          \
   case NV: {                                                                                                  \
     auto k = layernorm_bwd_kernel<TDY, TLP, NV>;                                                              \
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
     cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);    \
-    k<<<grid, LN_WARPS * 32, smem, s>>>(dy, x, gamma, mean, rstd, dres, dx, dx_lp, ws, want, rows, D);          \
+    k<<<grid, LN_WARPS * 32, smem, s>>>(dy, x, gamma, mean, rstd, dres, dx, dx_lp, ws, want, want_cs, rows, D);  \
   } break;
   switch (nv4) {
     LNB_CASE(1) LNB_CASE(2) LNB_CASE(3) LNB_CASE(4) LNB_CASE(5) LNB_CASE(6) LNB_CASE(7) LNB_CASE(8)
@@ -247,8 +257,8 @@ static int launch_ln_bwd(const TDY* dy, const float* x, const float* gamma, cons
   }
 #undef LNB_CASE
   AVJ_LAUNCH_CHECK();
-  if (want) {
-    layernorm_bwd_final_kernel<<<(2 * D + 31) / 32, 256, 0, s>>>(ws, grid, D, dgamma, dbeta);
+  if (want || want_cs) {
+    layernorm_bwd_final_kernel<<<(3 * D + 31) / 32, 256, 0, s>>>(ws, grid, D, dgamma, dbeta, dcolsum);
     AVJ_LAUNCH_CHECK();
   }
   return 0;
@@ -257,20 +267,20 @@ static int launch_ln_bwd(const TDY* dy, const float* x, const float* gamma, cons
 extern "C" int avj_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma,
                                  const float* mean, const float* rstd, const float* dres_in,
                                  float* dx_out, void* dx_lp, int lp_dtype,
-                                 float* dgamma, float* dbeta, float* ws,
+                                 float* dgamma, float* dbeta, float* dcolsum, float* ws,
                                  int rows, int D, void* stream) {
   AVJ_CHECK(D % 4 == 0 && D > 0, "avj_layernorm_bwd: D must be a positive multiple of 4");
-  AVJ_CHECK(!(dgamma || dbeta) || ws, "avj_layernorm_bwd: workspace required for dgamma/dbeta");
+  AVJ_CHECK(!(dgamma || dbeta || dcolsum) || ws, "avj_layernorm_bwd: workspace required for dgamma/dbeta/dcolsum");
   if (rows == 0) return 0;
   cudaStream_t s = as_stream(stream);
   AvjProfScope prof(AVJ_FAM_LN_BWD, (double)rows * D * ((dy_dtype == AVJ_BF16 ? 2 : 4) + 4 + (dres_in ? 4 : 0) + 4 +
                                                          (dx_lp ? (lp_dtype == AVJ_BF16 ? 2 : 4) : 0)), stream);
   if (dy_dtype == AVJ_BF16) {
     if (dx_lp && lp_dtype == AVJ_F32)
-      return launch_ln_bwd<bf16, float>((const bf16*)dy, x, gamma, mean, rstd, dres_in, dx_out, (float*)dx_lp, dgamma, dbeta, ws, rows, D, s);
-    return launch_ln_bwd<bf16, bf16>((const bf16*)dy, x, gamma, mean, rstd, dres_in, dx_out, (bf16*)dx_lp, dgamma, dbeta, ws, rows, D, s);
+      return launch_ln_bwd<bf16, float>((const bf16*)dy, x, gamma, mean, rstd, dres_in, dx_out, (float*)dx_lp, dgamma, dbeta, dcolsum, ws, rows, D, s);
+    return launch_ln_bwd<bf16, bf16>((const bf16*)dy, x, gamma, mean, rstd, dres_in, dx_out, (bf16*)dx_lp, dgamma, dbeta, dcolsum, ws, rows, D, s);
   }
   if (dx_lp && lp_dtype == AVJ_BF16)
-    return launch_ln_bwd<float, bf16>((const float*)dy, x, gamma, mean, rstd, dres_in, dx_out, (bf16*)dx_lp, dgamma, dbeta, ws, rows, D, s);
-  return launch_ln_bwd<float, float>((const float*)dy, x, gamma, mean, rstd, dres_in, dx_out, (float*)dx_lp, dgamma, dbeta, ws, rows, D, s);
+    return launch_ln_bwd<float, bf16>((const float*)dy, x, gamma, mean, rstd, dres_in, dx_out, (bf16*)dx_lp, dgamma, dbeta, dcolsum, ws, rows, D, s);
+  return launch_ln_bwd<float, float>((const float*)dy, x, gamma, mean, rstd, dres_in, dx_out, (float*)dx_lp, dgamma, dbeta, dcolsum, ws, rows, D, s);
 }

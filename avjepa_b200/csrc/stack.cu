@@ -61,8 +61,11 @@ extern "C" int avj_stack_backward(const avj_stack* s, const avj_layer* L, const 
   for (int i = s->L - 1; i >= 0; --i) {
     const avj_layer& w = L[i];
     AVJ_CHECK(w.pre != nullptr, "avj_stack_backward: layer %d has no saved pre-activation (forward ran without save)", i);
+    // Bias gradients: fc2.gb / proj.gb are column sums of the residual-stream gradient and come out of the
+    // LayerNorm backward that PRODUCES that gradient (dcolsum); only the top layer's fc2.gb, whose input was
+    // produced outside this call, needs its own pass.  fc1.gb / qkv.gb share one launch per layer.
     // ---- MLP: x2 = x1 + fc2(gelu(fc1(LN2(x1))))
-    if (w.fc2.gb) RC(avj_colsum(sc->dx_lp, cd, D, ident, w.fc2.gb, R, D, sc->ws, stream));
+    if (w.fc2.gb && i == s->L - 1) RC(avj_colsum(sc->dx_lp, cd, D, ident, w.fc2.gb, R, D, sc->ws, stream));
     avj_epilogue e;
     if (w.fc2.gw) {
       e = epi(AVJ_F32); e.accumulate = 1;
@@ -70,17 +73,16 @@ extern "C" int avj_stack_backward(const avj_stack* s, const avj_layer* L, const 
     }
     e = epi(cd); e.dact_aux = w.pre;
     RC(avj_gemm(cd, AVJ_GEMM_NN, sc->dx_lp, w.fc2.w, sc->d_hid, R, Hd, D, D, Hd, Hd, &e, stream));
-    if (w.fc1.gb) RC(avj_colsum(sc->d_hid, cd, Hd, ident, w.fc1.gb, R, Hd, sc->ws, stream));
     if (w.fc1.gw) {
       e = epi(AVJ_F32); e.accumulate = 1;
       RC(avj_gemm(cd, AVJ_GEMM_TN, sc->d_hid, w.h2, w.fc1.gw, Hd, D, R, Hd, D, D, &e, stream));
     }
     e = epi(cd);
     RC(avj_gemm(cd, AVJ_GEMM_NN, sc->d_hid, w.fc1.w, sc->d_h, R, D, Hd, Hd, D, D, &e, stream));
-    RC(avj_layernorm_bwd(sc->d_h, cd, w.x1, w.n2.w, w.mean2, w.rstd2, cur, nxt, sc->dx_lp, cd, w.n2.gw, w.n2.gb, sc->ws, R, D, stream));
+    RC(avj_layernorm_bwd(sc->d_h, cd, w.x1, w.n2.w, w.mean2, w.rstd2, cur, nxt, sc->dx_lp, cd, w.n2.gw, w.n2.gb, w.proj.gb,
+                         sc->ws, R, D, stream));
     { float* t = cur; cur = nxt; nxt = t; }
     // ---- attention: x1 = x + proj(attn(qkv(LN1(x))))
-    if (w.proj.gb) RC(avj_colsum(sc->dx_lp, cd, D, ident, w.proj.gb, R, D, sc->ws, stream));
     if (w.proj.gw) {
       e = epi(AVJ_F32); e.accumulate = 1;
       RC(avj_gemm(cd, AVJ_GEMM_TN, sc->dx_lp, w.o, w.proj.gw, D, D, R, D, D, D, &e, stream));
@@ -88,14 +90,20 @@ extern "C" int avj_stack_backward(const avj_stack* s, const avj_layer* L, const 
     e = epi(cd);
     RC(avj_gemm(cd, AVJ_GEMM_NN, sc->dx_lp, w.proj.w, sc->d_o, R, D, D, D, D, D, &e, stream));
     RC(avj_attention_bwd(cd, w.qkv_act, w.o, sc->d_o, w.lse, sc->d_qkv, sc->ws, s->B, s->N, s->H, hd, scale, stream));
-    if (w.qkv.gb) RC(avj_colsum(sc->d_qkv, cd, 3 * D, ident, w.qkv.gb, R, 3 * D, sc->ws, stream));
+    if (w.qkv.gb && w.fc1.gb) {
+      RC(avj_colsum2(sc->d_qkv, 3 * D, 3 * D, w.qkv.gb, sc->d_hid, Hd, Hd, w.fc1.gb, cd, R, sc->ws, stream));
+    } else {
+      if (w.qkv.gb) RC(avj_colsum(sc->d_qkv, cd, 3 * D, ident, w.qkv.gb, R, 3 * D, sc->ws, stream));
+      if (w.fc1.gb) RC(avj_colsum(sc->d_hid, cd, Hd, ident, w.fc1.gb, R, Hd, sc->ws, stream));
+    }
     if (w.qkv.gw) {
       e = epi(AVJ_F32); e.accumulate = 1;
       RC(avj_gemm(cd, AVJ_GEMM_TN, sc->d_qkv, w.h1, w.qkv.gw, 3 * D, D, R, 3 * D, D, D, &e, stream));
     }
     e = epi(cd);
     RC(avj_gemm(cd, AVJ_GEMM_NN, sc->d_qkv, w.qkv.w, sc->d_h, R, D, 3 * D, 3 * D, D, D, &e, stream));
-    RC(avj_layernorm_bwd(sc->d_h, cd, w.x, w.n1.w, w.mean1, w.rstd1, cur, nxt, sc->dx_lp, cd, w.n1.gw, w.n1.gb, sc->ws, R, D, stream));
+    RC(avj_layernorm_bwd(sc->d_h, cd, w.x, w.n1.w, w.mean1, w.rstd1, cur, nxt, sc->dx_lp, cd, w.n1.gw, w.n1.gb,
+                         i > 0 ? L[i - 1].fc2.gb : nullptr, sc->ws, R, D, stream));
     { float* t = cur; cur = nxt; nxt = t; }
   }
   // two swaps per layer: the result is back in dxa

@@ -112,8 +112,8 @@ def layernorm_fwd(x, gamma, beta, y, y_dtype, mean, rstd, rows, D, eps):
     _cabi.call('avj_layernorm_fwd', x, gamma, beta, y, y_dtype, mean, rstd, int(rows), int(D), float(eps), stream())
 
 
-def layernorm_bwd(dy, dy_dtype, x, gamma, mean, rstd, dres, dx, dx_lp, lp_dtype, dgamma, dbeta, ws, rows, D):
-    _cabi.call('avj_layernorm_bwd', dy, dy_dtype, x, gamma, mean, rstd, dres, dx, dx_lp, lp_dtype, dgamma, dbeta, ws,
+def layernorm_bwd(dy, dy_dtype, x, gamma, mean, rstd, dres, dx, dx_lp, lp_dtype, dgamma, dbeta, ws, rows, D, dcolsum=None):
+    _cabi.call('avj_layernorm_bwd', dy, dy_dtype, x, gamma, mean, rstd, dres, dx, dx_lp, lp_dtype, dgamma, dbeta, dcolsum, ws,
                int(rows), int(D), stream())
 
 
@@ -318,7 +318,7 @@ class StackRun(object):
     def scratch_bytes(self):
         R, D, Hd, s = self.R, self.D, self.Hd, self.mode.size
         per = 2 * _align(R * D * 4) + _align(R * D * s) + _align(R * Hd * s) + _align(R * 3 * D * s) + 2 * _align(R * D * s)
-        ws = max(_cabi.load().avj_layernorm_bwd_ws_floats(R, D), _cabi.load().avj_colsum_ws_floats(R, 3 * max(D, Hd)),
+        ws = max(_cabi.load().avj_layernorm_bwd_ws_floats(R, D), _cabi.load().avj_colsum_ws_floats(R, 3 * D + Hd),
                  _cabi.load().avj_attention_bwd_ws_floats(self.B, self.N, self.H, self.hd)) * 4
         return per + _align(ws) + (1 << 16)
 
@@ -336,7 +336,7 @@ class StackRun(object):
         d_h = sc.alloc(R * D * s)          # d LN-output (h2 / h1)
         d_o = sc.alloc(R * D * s)
         lib = _cabi.load()
-        ws = sc.alloc(4 * max(lib.avj_layernorm_bwd_ws_floats(R, D), lib.avj_colsum_ws_floats(R, 3 * max(D, Hd)),
+        ws = sc.alloc(4 * max(lib.avj_layernorm_bwd_ws_floats(R, D), lib.avj_colsum_ws_floats(R, 3 * D + Hd),
                               lib.avj_attention_bwd_ws_floats(self.B, self.N, self.H, self.hd)))
         cur, nxt = dxa, dxb
         if norm is not None:

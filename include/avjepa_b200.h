@@ -107,6 +107,10 @@ int avj_fill_mask_tokens(const float* mask_token, const float* pos, const int64_
 int64_t avj_colsum_ws_floats(int rows, int D);
 int avj_colsum(const void* in, int in_dtype, int ld, avj_rowmap map, float* out,
                int rows, int D, float* ws, void* stream);
+/* two column sums over the same rows in ONE launch (identity row map): out1[n] += sum_r in1[r, n] (D1
+ * columns, ld1) and out2 likewise.  ws: avj_colsum_ws_floats(rows, D1 + D2) floats. */
+int avj_colsum2(const void* in1, int ld1, int D1, float* out1, const void* in2, int ld2, int D2, float* out2,
+                int in_dtype, int rows, float* ws, void* stream);
 
 /* ---- K5: nn.LayerNorm (modules.py:115,119; eps 1e-6) and F.layer_norm without affine
  *      (app/avjepa/train.py:448; eps 1e-5).  x fp32 [rows, D]; y in y_dtype; gamma/beta may
@@ -115,13 +119,15 @@ int avj_layernorm_fwd(const float* x, const float* gamma, const float* beta,
                       void* y, int y_dtype, float* mean, float* rstd,
                       int rows, int D, float eps, void* stream);
 /* dx_out = dres_in + LN'(dy) (fp32);  dx_lp: optional low-precision copy of dx_out (dtype
- * lp_dtype) feeding the next dgrad/wgrad GEMM;  dgamma/dbeta are ACCUMULATED (may be NULL).
+ * lp_dtype) feeding the next dgrad/wgrad GEMM;  dgamma/dbeta are ACCUMULATED (may be NULL);
+ * dcolsum (may be NULL): dcolsum[n] += sum_r dx_out[r, n] -- the bias gradient of the Linear whose
+ * output is added to this residual stream (proj / fc2), fused here instead of a separate pass.
  * ws: avj_layernorm_bwd_ws_floats(rows, D) floats. */
 int64_t avj_layernorm_bwd_ws_floats(int rows, int D);
 int avj_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float* gamma,
                       const float* mean, const float* rstd, const float* dres_in,
                       float* dx_out, void* dx_lp, int lp_dtype,
-                      float* dgamma, float* dbeta, float* ws,
+                      float* dgamma, float* dbeta, float* dcolsum, float* ws,
                       int rows, int D, void* stream);
 
 /* ---- K7: F.scaled_dot_product_attention(q, k, v) (modules.py:66-69): non-causal, no

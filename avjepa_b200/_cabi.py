@@ -104,6 +104,7 @@ PROTOTYPES = {
     'avj_memset_zero': (_i, [_vp, _i64, _vp]),
     'avj_prof_enable': (_i, [_i]),
     'avj_prof_collect': (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    'avj_prof_dump': (_i, [C.c_char_p]),
     'avj_stack_forward': (_i, [C.POINTER(Stack), C.POINTER(Layer), _vp]),
     'avj_stack_backward': (_i, [C.POINTER(Stack), C.POINTER(Layer), C.POINTER(StackScratch), _vp]),
 }
@@ -154,11 +155,16 @@ def call(name, *args, launches=1):
     check(getattr(lib, name)(*args), name)
 
 
-PROF_FAMILIES = ('gemm', 'attention_fwd', 'attention_bwd', 'layernorm_fwd', 'layernorm_bwd', 'colsum', 'optimizer')
+PROF_FAMILIES = ('gemm', 'attention_fwd', 'attention_bwd', 'layernorm_fwd', 'layernorm_bwd', 'colsum', 'optimizer', 'other')
 
 
 def prof_enable(on):
     check(load().avj_prof_enable(1 if on else 0), 'avj_prof_enable')
+
+
+def prof_dump(path):
+    """CSV of every timed launch since prof_enable(True): family,work,ms,d0..d3 (include/avjepa_b200.h)."""
+    check(load().avj_prof_dump(str(path).encode()), 'avj_prof_dump')
 
 
 def prof_collect():

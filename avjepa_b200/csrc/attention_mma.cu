@@ -226,16 +226,27 @@ fa_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __res
 // ============================================================================ backward
 // delta[b,h,i] = sum_d dO . O  -- one THREAD per (b, i, h): a head slice is hd contiguous bf16 (48..256 B),
 // read as 16-byte vectors; consecutive threads take consecutive heads, i.e. consecutive memory.
+// Legacy form (lse2_out == NULL): delta[(b*H+h)*N + i], unscaled (mma.sync / SIMT backward).
+// tcgen05 form: rows padded to n_pad (multiple of 64, zero filled) so the backward kernels can read whole
+// float4 groups without guards; delta is pre-multiplied by `scale` and lse by log2(e).
 __global__ void __launch_bounds__(256)
 fa_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, float* __restrict__ delta,
+                const float* __restrict__ lse, float* __restrict__ lse2_out, float scale, int n_pad,
                 int B, int N, int H, int hd) {
-  const int64_t total = (int64_t)B * N * H;
+  const int64_t total = (int64_t)B * n_pad * H;
   for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < total; w += (int64_t)gridDim.x * blockDim.x) {
     const int h = (int)(w % H);
     const int64_t bn = w / H;
-    const int i = (int)(bn % N), b = (int)(bn / N);
-    const bf16* o = out + w * hd;
-    const bf16* g = dout + w * hd;
+    const int i = (int)(bn % n_pad), b = (int)(bn / n_pad);
+    const int64_t oi = ((int64_t)b * H + h) * n_pad + i;
+    if (i >= N) {
+      delta[oi] = 0.f;
+      if (lse2_out) lse2_out[oi] = 0.f;
+      continue;
+    }
+    const int64_t row = ((int64_t)b * N + i) * H + h;
+    const bf16* o = out + row * hd;
+    const bf16* g = dout + row * hd;
     float s = 0.f;
     if ((hd & 7) == 0) {
       for (int d = 0; d < hd; d += 8) {
@@ -248,7 +259,8 @@ fa_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, flo
     } else {
       for (int d = 0; d < hd; ++d) s = fmaf(__bfloat162float(o[d]), __bfloat162float(g[d]), s);
     }
-    delta[((int64_t)b * H + h) * N + i] = s;
+    delta[oi] = s * scale;
+    if (lse2_out) lse2_out[oi] = lse[((int64_t)b * H + h) * N + i] * 1.4426950408889634f;
   }
 }
 
@@ -468,13 +480,16 @@ static int fwd_launch(const bf16* qkv, bf16* out, float* lse, int B, int N, int 
   return 0;
 }
 
-// delta[b,h,i] = sum_d dO . O into `delta` ([B, H, N] fp32); shared with the tcgen05 backward.
-int avj_attention_delta(const void* out, const void* dout, float* delta, int B, int N, int H, int hd, cudaStream_t s) {
-  const int64_t threads = (int64_t)B * N * H;
+// Row statistics of the backward: delta = rowsum(dO . O) and (tcgen05 path) lse * log2(e).
+//   lse2_out == NULL : delta [B, H, N], unscaled
+//   lse2_out != NULL : delta * scale and lse2 as [B, H, n_pad] with zero padding (n_pad % 64 == 0)
+int avj_attention_delta(const void* out, const void* dout, float* delta, const float* lse, float* lse2_out, float scale,
+                        int n_pad, int B, int N, int H, int hd, cudaStream_t s) {
+  const int64_t threads = (int64_t)B * n_pad * H;
   int grid = (int)((threads + 255) / 256);
   const int cap = avj_num_sms() * 16;
   if (grid > cap) grid = cap;
-  fa_delta_kernel<<<grid, 256, 0, s>>>((const bf16*)out, (const bf16*)dout, delta, B, N, H, hd);
+  fa_delta_kernel<<<grid, 256, 0, s>>>((const bf16*)out, (const bf16*)dout, delta, lse, lse2_out, scale, n_pad, B, N, H, hd);
   AVJ_LAUNCH_CHECK();
   return 0;
 }
@@ -483,12 +498,8 @@ template <int HP>
 static int bwd_launch(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, float* ws,
                       int B, int N, int H, int hd, float scale, cudaStream_t s) {
   {
-    const int64_t warps = (int64_t)B * N * H;
-    int grid = (int)((warps + 7) / 8);
-    const int cap = avj_num_sms() * 16;
-    if (grid > cap) grid = cap;
-    fa_delta_kernel<<<grid, 256, 0, s>>>(out, dout, ws, B, N, H, hd);
-    AVJ_LAUNCH_CHECK();
+    int rc = avj_attention_delta(out, dout, ws, nullptr, nullptr, 1.0f, N, B, N, H, hd, s);
+    if (rc) return rc;
   }
   const size_t smem_dq = (size_t)(2 * FA_BM + 4 * FA_BN) * (HP + 8) * sizeof(bf16);
   const size_t smem_dkv = smem_dq + 4 * FA_BN * sizeof(float);

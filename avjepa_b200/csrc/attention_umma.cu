@@ -68,10 +68,15 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
   const uint32_t p_full = bars + 80;        // count 128
   const uint32_t o_done = bars + 88;        // count 1
   const uint32_t tmem_slot = bars + 96;
+  const uint32_t q_ready = bars + 104;      // count 32: Q pad columns zeroed (TMA path, hd < HDP)
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(ua_raw + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * UA_BM;
+  // A TMA box always spans HDP columns: for hd < HDP columns [hd, HDP) of every tile hold the NEXT head's
+  // values.  They only matter in the contraction of S = Q K^T, so zeroing them in the Q tile is enough; the
+  // matching columns of O = P V are computed from V's neighbour and never stored.
+  const bool zero_q_pad = TMA && hd < HDP;
   const int64_t rs = 3 * (int64_t)H * hd;
   const bf16* qb = qkv + (int64_t)b * N * rs + (int64_t)h * hd;
   const bf16* kb = qb + (int64_t)H * hd;
@@ -82,6 +87,7 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
     if (base & 1023u) __trap();                      // SWIZZLE_128B tiles need 1024-byte alignment
     for (int i = 0; i < NST; ++i) { ua_mbar_init(kv_full + 8 * i, TMA ? 1 : UA_LOADERS); ua_mbar_init(kv_empty + 8 * i, 1); }
     ua_mbar_init(s_full, 1); ua_mbar_init(s_free, 128); ua_mbar_init(p_full, 128); ua_mbar_init(o_done, 1);
+    ua_mbar_init(q_ready, 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -132,6 +138,13 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
       ua_fence_async_smem();
       for (int j = max(0, T - (NST - 1)); j < T; ++j) ua_mbar_arrive(kv_full + 8 * (j % NST));
     }
+  } else if (TMA && warp == 2) {
+    if (zero_q_pad) {
+      ua_mbar_wait(kv_full, 0);                                       // Q (and tile 0) have landed
+      ua_zero_pad<HDP>(sQ, 128, hd, lane);
+      ua_fence_async_smem();
+      ua_mbar_arrive(q_ready);
+    }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
     if (lane == 0) {
@@ -145,6 +158,7 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
         ua_commit(s_full);
       };
       ua_mbar_wait(kv_full, 0);   // tile 0 (and Q)
+      if (zero_q_pad) ua_mbar_wait(q_ready, 0);
       ua_fence_after();
       issue_s(0);
       for (int t = 0; t < T; ++t) {
@@ -276,15 +290,18 @@ typedef CUresult (*PFN_ua_encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// [B, N, cols] bf16 viewed as a 3-D tensor {cols, N, B}; box = {64 cols, box_rows rows, 1}, SWIZZLE_128B.
-int ua_make_map3d(const void* qkv, int B, int N, int cols, int box_rows, CUtensorMap* out) {
-  struct Key { const void* p; int B, N, cols, box_rows; };
+// [B, N, cols] bf16 viewed as a 3-D tensor {cols, N, B}; box = {box_cols cols, box_rows rows, 1}:
+// 64 columns -> 128-byte rows, SWIZZLE_128B; 32 columns -> 64-byte rows, SWIZZLE_64B (UaTile<32>).
+int ua_make_map3d(const void* qkv, int B, int N, int cols, int box_rows, CUtensorMap* out, int box_cols) {
+  struct Key { const void* p; int B, N, cols, box_rows, box_cols; };
+  AVJ_CHECK(box_cols == 32 || box_cols == 64, "ua_make_map3d: box_cols must be 32 or 64");
   static std::mutex mu;
   static std::vector<std::pair<Key, CUtensorMap>> cache;
   {
     std::lock_guard<std::mutex> g(mu);
     for (auto& e : cache)
-      if (e.first.p == qkv && e.first.B == B && e.first.N == N && e.first.cols == cols && e.first.box_rows == box_rows) { *out = e.second; return 0; }
+      if (e.first.p == qkv && e.first.B == B && e.first.N == N && e.first.cols == cols && e.first.box_rows == box_rows &&
+          e.first.box_cols == box_cols) { *out = e.second; return 0; }
   }
   static PFN_ua_encode enc = nullptr;
   if (!enc) {
@@ -297,15 +314,16 @@ int ua_make_map3d(const void* qkv, int B, int N, int cols, int box_rows, CUtenso
   AVJ_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)N, (cuuint64_t)B};
   cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)cols * 2 * (cuuint64_t)N};
-  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   AVJ_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(qkv) failed (%d)", (int)r);
   std::lock_guard<std::mutex> g(mu);
   if (cache.size() > 512) cache.clear();
-  cache.push_back({Key{qkv, B, N, cols, box_rows}, *out});
+  cache.push_back({Key{qkv, B, N, cols, box_rows, box_cols}, *out});
   return 0;
 }
 
@@ -322,7 +340,7 @@ static int ua_launch(const bf16* qkv, bf16* out, float* lse, int B, int N, int H
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
   if (TMA) {
-    int rc = ua_make_map3d(qkv, B, N, 3 * H * hd, 128, &map);
+    int rc = ua_make_map3d(qkv, B, N, 3 * H * hd, 128, &map, HDP);
     if (rc) return rc;
   }
   dim3 grid((N + UA_BM - 1) / UA_BM, H, B);
@@ -334,7 +352,11 @@ static int ua_launch(const bf16* qkv, bf16* out, float* lse, int B, int N, int H
 int avj_attention_fwd_umma(const void* qkv, void* out, float* lse, int B, int N, int H, int hd, float scale, cudaStream_t s) {
   static int use_tma = -1;
   if (use_tma < 0) { const char* e = getenv("AVJ_ATTN_TMA"); use_tma = (e && e[0] == '0') ? 0 : 1; }
-  if (hd <= 32) return ua_launch<32, false>((const bf16*)qkv, (bf16*)out, lse, B, N, H, hd, scale, s);
+  if (hd <= 32) {
+    if (use_tma && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0)
+      return ua_launch<32, true>((const bf16*)qkv, (bf16*)out, lse, B, N, H, hd, scale, s);
+    return ua_launch<32, false>((const bf16*)qkv, (bf16*)out, lse, B, N, H, hd, scale, s);
+  }
   if (hd == 64 && use_tma && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0)
     return ua_launch<64, true>((const bf16*)qkv, (bf16*)out, lse, B, N, H, hd, scale, s);
   return ua_launch<64, false>((const bf16*)qkv, (bf16*)out, lse, B, N, H, hd, scale, s);

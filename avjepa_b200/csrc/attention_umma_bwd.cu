@@ -51,22 +51,21 @@
 // Streamed-tile ring depth.  The stage of tile t is only released by the OUTPUT MMAs of step t, so with 2
 // stages the load of tile t+2 starts when step t ends and its full L2 latency is exposed every step; 3-4
 // stages issue it one or two steps earlier.  hd <= 32 tiles are half the size (64-byte rows) so 4 stages
-// fit next to a second CTA; at hd = 64 the dK/dV pass only has room for 2.
+// fit next to a second CTA; at hd = 64 there is room for 3 (112 KB per CTA in the dK/dV pass).
 template <int HDP, bool KV> struct UbSmem {
-  static constexpr int NST = HDP == 32 ? 4 : (KV ? 2 : 3);
+  static constexpr int NST = HDP == 32 ? 4 : 3;
   static constexpr uint32_t ROW_TILE = 128 * UaTile<HDP>::PITCH, COL_TILE = 64 * UaTile<HDP>::PITCH;
   static constexpr uint32_t R1 = 0, R2 = ROW_TILE, C1 = 2 * ROW_TILE, C2 = C1 + NST * COL_TILE,
                             DS = C2 + NST * COL_TILE, P = DS + UB_PD_TILE,
-                            STAT = KV ? P + UB_PD_TILE : P,             // [NST][lse2 64 | delta 64] floats
-                            BARS = STAT + (KV ? NST * 512 : 0), TOTAL = BARS + 128;
+                            BARS = KV ? P + UB_PD_TILE : P, TOTAL = BARS + 128;
 };
 
 template <int HDP, bool TMA, bool KV>
 __global__ void __launch_bounds__(UB_THREADS, 2)
 fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_constant__ CUtensorMap map_qkv64,
                    const __grid_constant__ CUtensorMap map_do, const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
-                   const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv,
-                   int N, int H, int hd, float scale, float scale_log2) {
+                   const float* __restrict__ lse2, const float* __restrict__ delta, bf16* __restrict__ dqkv,
+                   int N, int n_pad, int H, int hd, float scale, float scale_log2) {
   using L = UbSmem<HDP, KV>;
   using TL = UaTile<HDP>;
   constexpr int NST = L::NST;
@@ -82,8 +81,8 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
   const uint32_t p_full = bars + 80;
   const uint32_t o_done = bars + 88;
   const uint32_t tmem_slot = bars + 96;
+  const uint32_t r_ready = bars + 104;      // count 32: pad columns of the stationary tiles zeroed (TMA, hd < HDP)
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(ub_raw + L::BARS + 96);
-  float* stat = reinterpret_cast<float*>(ub_raw + L::STAT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, r0 = blockIdx.x * UB_BM;
@@ -93,12 +92,18 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
   const bf16* kb = qb + (int64_t)H * hd;
   const bf16* vb = kb + (int64_t)H * hd;
   const bf16* dob = dout + (int64_t)b * N * os + (int64_t)h * hd;
-  const float* lse_bh = lse + ((int64_t)b * H + h) * N;
-  const float* delta_bh = delta + ((int64_t)b * H + h) * N;
+  // row statistics prepared by fa_delta_kernel: lse * log2(e) and delta * scale, rows padded to n_pad
+  const float* lse_bh = lse2 + ((int64_t)b * H + h) * n_pad;
+  const float* delta_bh = delta + ((int64_t)b * H + h) * n_pad;
   const int T = (N + UB_BN - 1) / UB_BN;
+  // A TMA box always spans HDP columns: for hd < HDP columns [hd, HDP) hold the neighbouring head.  Both score
+  // products contract over those columns with one STATIONARY operand (S: R1, dP: R2), so zeroing the pads of
+  // R1 / R2 once per CTA is enough; the pad columns of dQ / dK / dV are never stored.
+  const bool zero_pad = TMA && hd < HDP;
 
   if (threadIdx.x == 0) {
     if (base & 1023u) __trap();
+    ua_mbar_init(r_ready, 32);
     for (int i = 0; i < NST; ++i) { ua_mbar_init(c_full + 8 * i, TMA ? 1 : UB_LOADERS); ua_mbar_init(c_empty + 8 * i, 1); }
     ua_mbar_init(t_full, 1); ua_mbar_init(t_free, 128); ua_mbar_init(p_full, 128); ua_mbar_init(o_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -138,14 +143,6 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
         ua_mbar_arrive(c_full + 8 * ((t - (NST - 1)) % NST));
       }
       if (t >= NST) ua_mbar_wait(c_empty + 8 * st, ((t / NST) & 1) ^ 1);
-      if (KV) {                                               // per-column statistics of this query tile
-        for (int i = ld_tid; i < UB_BN; i += ld_n) {
-          const int qi = t * UB_BN + i;
-          stat[st * 128 + i] = qi < N ? lse_bh[qi] * 1.4426950408889634f : 0.f;
-          stat[st * 128 + 64 + i] = qi < N ? delta_bh[qi] * scale : 0.f;     // pre-scaled: dS = P (scale dP - scale delta)
-        }
-        __syncwarp();
-      }
       const uint32_t c1 = sC1 + st * L::COL_TILE, c2 = sC2 + st * L::COL_TILE;
       if (TMA) {
         if (lane == 0) {
@@ -172,6 +169,14 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
       ua_fence_async_smem();
       for (int j = max(0, T - (NST - 1)); j < T; ++j) ua_mbar_arrive(c_full + 8 * (j % NST));
     }
+  } else if (TMA && warp == 2) {
+    if (zero_pad) {
+      ua_mbar_wait(c_full, 0);                                  // R1, R2 (and tile 0) have landed
+      ua_zero_pad<HDP>(sR1, 128, hd, lane);
+      ua_zero_pad<HDP>(sR2, 128, hd, lane);
+      ua_fence_async_smem();
+      ua_mbar_arrive(r_ready);
+    }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
     if (lane == 0) {
@@ -188,6 +193,7 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
         ua_commit(t_full);
       };
       ua_mbar_wait(c_full, 0);
+      if (zero_pad) ua_mbar_wait(r_ready, 0);
       ua_fence_after();
       issue_scores(0);
       for (int t = 0; t < T; ++t) {
@@ -227,7 +233,7 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
     const uint32_t t_1 = tmem + ((uint32_t)(q * 32) << 16);
     const int ri = r0 + row;
     float my_l2 = 0.f, my_dl = 0.f;
-    if (!KV && ri < N) { my_l2 = lse_bh[ri] * 1.4426950408889634f; my_dl = delta_bh[ri] * scale; }
+    if (!KV && ri < N) { my_l2 = lse_bh[ri]; my_dl = delta_bh[ri]; }
     for (int t = 0; t < T; ++t) {
       ua_mbar_wait(t_full, t & 1);
       ua_fence_after();
@@ -238,14 +244,20 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
       ua_fence_before();
       ua_mbar_arrive(t_free);
       uint32_t pk_p[KV ? 32 : 1], pk_d[32];
-      const float* st_l2 = stat + (t % NST) * 128;
-      if (KV) ua_mbar_wait(c_full + 8 * (t % NST), (t / NST) & 1);   // acquire the loader's lse/delta stores
+      // per-column statistics of this query tile straight from global memory: every thread of the CTA reads
+      // the same 2 x 256 bytes (L1 broadcast); the next tile's lines are prefetched while this one computes
+      const float* st_l2 = lse_bh + t * UB_BN;
+      const float* st_dl = delta_bh + t * UB_BN;
+      if (KV && t + 1 < T && lane < 4) {
+        const float* pf = (lane < 2 ? st_l2 : st_dl) + UB_BN + (lane & 1) * 32;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+      }
 #pragma unroll
       for (int j = 0; j < 64; j += 4) {
         float l2[4], dl[4];
         if constexpr (KV) {
-          const float4 a = *reinterpret_cast<const float4*>(st_l2 + j);
-          const float4 d = *reinterpret_cast<const float4*>(st_l2 + 64 + j);
+          const float4 a = __ldg(reinterpret_cast<const float4*>(st_l2 + j));
+          const float4 d = __ldg(reinterpret_cast<const float4*>(st_dl + j));
           l2[0] = a.x; l2[1] = a.y; l2[2] = a.z; l2[3] = a.w;
           dl[0] = d.x; dl[1] = d.y; dl[2] = d.z; dl[3] = d.w;
         } else {
@@ -256,7 +268,7 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           p[e] = ua_exp2(fmaf(s[j + e], scale_log2, -l2[e]));
-          ds[e] = p[e] * fmaf(dp[j + e], scale, -dl[e]);
+          ds[e] = p[e] * fmaf(dp[j + e], scale, -dl[e]);          // dl is pre-multiplied by scale
         }
         if constexpr (KV) { pk_p[j >> 1] = pack_bf16x2(p[0], p[1]); pk_p[(j >> 1) + 1] = pack_bf16x2(p[2], p[3]); }
         pk_d[j >> 1] = pack_bf16x2(ds[0], ds[1]); pk_d[(j >> 1) + 1] = pack_bf16x2(ds[2], ds[3]);
@@ -315,8 +327,9 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
 // ------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------
-int avj_attention_delta(const void* out, const void* dout, float* delta, int B, int N, int H, int hd, cudaStream_t s);
-int ua_make_map3d(const void* ptr, int B, int N, int cols, int box_rows, CUtensorMap* out);
+int avj_attention_delta(const void* out, const void* dout, float* delta, const float* lse, float* lse2_out, float scale,
+                        int n_pad, int B, int N, int H, int hd, cudaStream_t s);
+int ua_make_map3d(const void* ptr, int B, int N, int cols, int box_rows, CUtensorMap* out, int box_cols);
 
 bool avj_attention_umma_bwd_supported(int dtype, int hd) {
   return dtype == AVJ_BF16 && hd % 8 == 0 && hd >= 8 && hd <= 64;
@@ -324,7 +337,8 @@ bool avj_attention_umma_bwd_supported(int dtype, int hd) {
 
 template <int HDP, bool TMA, bool KV>
 static int ub_launch(const CUtensorMap& m128, const CUtensorMap& m64, const CUtensorMap& mdo, const bf16* qkv, const bf16* dout,
-                     const float* lse, const float* delta, bf16* dqkv, int B, int N, int H, int hd, float scale, cudaStream_t s) {
+                     const float* lse2, const float* delta, bf16* dqkv, int B, int N, int n_pad, int H, int hd, float scale,
+                     cudaStream_t s) {
   static bool set = false;
   const int smem = (int)UbSmem<HDP, KV>::TOTAL;
   if (!set) {
@@ -334,38 +348,46 @@ static int ub_launch(const CUtensorMap& m128, const CUtensorMap& m64, const CUte
     set = true;
   }
   dim3 grid((N + UB_BM - 1) / UB_BM, H, B);
-  fa_bwd_umma_kernel<HDP, TMA, KV><<<grid, UB_THREADS, smem, s>>>(m128, m64, mdo, qkv, dout, lse, delta, dqkv, N, H, hd, scale,
+  fa_bwd_umma_kernel<HDP, TMA, KV><<<grid, UB_THREADS, smem, s>>>(m128, m64, mdo, qkv, dout, lse2, delta, dqkv, N, n_pad, H, hd, scale,
                                                                   scale * 1.4426950408889634f);
   AVJ_LAUNCH_CHECK();
   return 0;
 }
 
 template <int HDP, bool TMA>
-static int ub_both(const bf16* qkv, const bf16* dout, const float* lse, const float* delta, bf16* dqkv,
-                   int B, int N, int H, int hd, float scale, cudaStream_t s) {
+static int ub_both(const bf16* qkv, const bf16* dout, const float* lse2, const float* delta, bf16* dqkv,
+                   int B, int N, int n_pad, int H, int hd, float scale, cudaStream_t s) {
   CUtensorMap m128, m64, mdo64, mdo128;
   memset(&m128, 0, sizeof(m128)); memset(&m64, 0, sizeof(m64)); memset(&mdo64, 0, sizeof(mdo64)); memset(&mdo128, 0, sizeof(mdo128));
   if (TMA) {
     int rc;
-    if ((rc = ua_make_map3d(qkv, B, N, 3 * H * hd, 128, &m128))) return rc;
-    if ((rc = ua_make_map3d(qkv, B, N, 3 * H * hd, 64, &m64))) return rc;
-    if ((rc = ua_make_map3d(dout, B, N, H * hd, 64, &mdo64))) return rc;
-    if ((rc = ua_make_map3d(dout, B, N, H * hd, 128, &mdo128))) return rc;
+    if ((rc = ua_make_map3d(qkv, B, N, 3 * H * hd, 128, &m128, HDP))) return rc;
+    if ((rc = ua_make_map3d(qkv, B, N, 3 * H * hd, 64, &m64, HDP))) return rc;
+    if ((rc = ua_make_map3d(dout, B, N, H * hd, 64, &mdo64, HDP))) return rc;
+    if ((rc = ua_make_map3d(dout, B, N, H * hd, 128, &mdo128, HDP))) return rc;
   }
-  int rc = ub_launch<HDP, TMA, true>(m128, m64, mdo64, qkv, dout, lse, delta, dqkv, B, N, H, hd, scale, s);
+  int rc = ub_launch<HDP, TMA, true>(m128, m64, mdo64, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
   if (rc) return rc;
-  return ub_launch<HDP, TMA, false>(m128, m64, mdo128, qkv, dout, lse, delta, dqkv, B, N, H, hd, scale, s);
+  return ub_launch<HDP, TMA, false>(m128, m64, mdo128, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
 }
 
 int avj_attention_bwd_umma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* ws,
                            int B, int N, int H, int hd, float scale, cudaStream_t s) {
-  int rc = avj_attention_delta(out, dout, ws, B, N, H, hd, s);
+  // workspace: delta * scale | lse * log2(e), each [B, H, n_pad]
+  const int n_pad = (N + 63) / 64 * 64;
+  float* delta = ws;
+  float* lse2 = ws + (int64_t)B * H * n_pad;
+  int rc = avj_attention_delta(out, dout, delta, lse, lse2, scale, n_pad, B, N, H, hd, s);
   if (rc) return rc;
   static int use_tma = -1;
   if (use_tma < 0) { const char* e = getenv("AVJ_ATTN_TMA"); use_tma = (e && e[0] == '0') ? 0 : 1; }
   const bool aligned = ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(dout)) & 15) == 0;
-  if (hd <= 32) return ub_both<32, false>((const bf16*)qkv, (const bf16*)dout, lse, ws, (bf16*)dqkv, B, N, H, hd, scale, s);
+  if (hd <= 32) {
+    if (use_tma && aligned)
+      return ub_both<32, true>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, B, N, n_pad, H, hd, scale, s);
+    return ub_both<32, false>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, B, N, n_pad, H, hd, scale, s);
+  }
   if (hd == 64 && use_tma && aligned)
-    return ub_both<64, true>((const bf16*)qkv, (const bf16*)dout, lse, ws, (bf16*)dqkv, B, N, H, hd, scale, s);
-  return ub_both<64, false>((const bf16*)qkv, (const bf16*)dout, lse, ws, (bf16*)dqkv, B, N, H, hd, scale, s);
+    return ub_both<64, true>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, B, N, n_pad, H, hd, scale, s);
+  return ub_both<64, false>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, B, N, n_pad, H, hd, scale, s);
 }

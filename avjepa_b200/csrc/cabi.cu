@@ -10,17 +10,18 @@
 // ---- kernel timing ---------------------------------------------------------------------------
 bool g_avj_prof_on = false;
 namespace {
-struct ProfRec { cudaEvent_t a, b; int family; double work; };
+struct ProfRec { cudaEvent_t a, b; int family; double work; int d[4]; };
 std::vector<ProfRec> g_prof;
 std::mutex g_prof_mu;
 thread_local int t_prof_open = -1;
 }  // namespace
 
-void avj_prof_begin(int family, double work, cudaStream_t s) {
+void avj_prof_begin(int family, double work, cudaStream_t s, int d0, int d1, int d2, int d3) {
   std::lock_guard<std::mutex> g(g_prof_mu);
   if (t_prof_open >= 0) return;                    // nested entry point: the outer scope owns the record
   ProfRec r;
   r.family = family; r.work = work;
+  r.d[0] = d0; r.d[1] = d1; r.d[2] = d2; r.d[3] = d3;
   if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
   cudaEventRecord(r.a, s);
   g_prof.push_back(r);
@@ -55,6 +56,21 @@ extern "C" int avj_prof_collect(int family, double* ms, double* work, int* launc
   if (ms) *ms = t;
   if (work) *work = w;
   if (launches) *launches = n;
+  return 0;
+}
+// One CSV line per record (family, work, ms, d0..d3) in launch order -- tools/step_breakdown.py groups them by shape.
+extern "C" int avj_prof_dump(const char* path) {
+  std::lock_guard<std::mutex> g(g_prof_mu);
+  AVJ_CHECK(path != nullptr, "avj_prof_dump: NULL path");
+  FILE* f = fopen(path, "w");
+  AVJ_CHECK(f != nullptr, "avj_prof_dump: cannot open %s", path);
+  fprintf(f, "family,work,ms,d0,d1,d2,d3\n");
+  for (auto& r : g_prof) {
+    float e = 0.f;
+    if (cudaEventSynchronize(r.b) != cudaSuccess || cudaEventElapsedTime(&e, r.a, r.b) != cudaSuccess) { cudaGetLastError(); continue; }
+    fprintf(f, "%d,%.6g,%.6f,%d,%d,%d,%d\n", r.family, r.work, e, r.d[0], r.d[1], r.d[2], r.d[3]);
+  }
+  fclose(f);
   return 0;
 }
 
@@ -115,7 +131,9 @@ extern "C" int avj_gemm(int dtype, int layout, const void* A, const void* B, voi
     AVJ_CHECK(ep.accumulate, "avj_gemm: K == 0 is only meaningful for accumulate epilogues");
     return 0;
   }
-  AvjProfScope prof(AVJ_FAM_GEMM, 2.0 * M * (double)N * K, stream);
+  const int epi_bits = layout | (ep.bias ? 4 : 0) | (ep.act ? 8 : 0) | (ep.residual ? 16 : 0) | (ep.accumulate ? 32 : 0) |
+                       (ep.dact_aux ? 64 : 0) | (ep.out_dtype == AVJ_F32 ? 128 : 0);
+  AvjProfScope prof(AVJ_FAM_GEMM, 2.0 * M * (double)N * K, stream, epi_bits, M, N, K);
   if (!force_simt() && avj_gemm_umma_supported(dtype, layout, A, B, M, N, K, lda, ldb, ep))
     return avj_gemm_umma(layout, A, B, C, M, N, K, lda, ldb, ldc, ep, as_stream(stream));
   return avj_gemm_simt(dtype, layout, A, B, C, M, N, K, lda, ldb, ldc, ep, as_stream(stream));
@@ -123,14 +141,14 @@ extern "C" int avj_gemm(int dtype, int layout, const void* A, const void* B, voi
 
 extern "C" int64_t avj_attention_bwd_ws_floats(int B, int N, int H, int hd) {
   (void)hd;
-  return (int64_t)B * H * N;   // delta
+  return 2 * (int64_t)B * H * ((N + 63) / 64 * 64);   // delta and lse*log2(e), rows padded to 64
 }
 
 extern "C" int avj_attention_fwd(int dtype, const void* qkv, void* out, float* lse,
                                  int B, int N, int H, int hd, float scale, void* stream) {
   AVJ_CHECK(hd > 0 && hd <= 128, "avj_attention_fwd: head_dim %d out of range (1..128)", hd);
   if (B == 0 || N == 0) return 0;
-  AvjProfScope prof(AVJ_FAM_ATTN_FWD, 4.0 * B * H * (double)N * N * hd, stream);
+  AvjProfScope prof(AVJ_FAM_ATTN_FWD, 4.0 * B * H * (double)N * N * hd, stream, B, N, H, hd);
   if (!force_simt_attn() && attn_fwd_use_umma() && avj_attention_umma_fwd_supported(dtype, hd))
     return avj_attention_fwd_umma(qkv, out, lse, B, N, H, hd, scale, as_stream(stream));
   if (!force_simt_attn() && avj_attention_mma_supported(dtype, hd))
@@ -144,7 +162,7 @@ extern "C" int avj_attention_bwd(int dtype, const void* qkv, const void* out, co
   AVJ_CHECK(hd > 0 && hd <= 128, "avj_attention_bwd: head_dim %d out of range (1..128)", hd);
   AVJ_CHECK(ws != nullptr, "avj_attention_bwd: workspace required");
   if (B == 0 || N == 0) return 0;
-  AvjProfScope prof(AVJ_FAM_ATTN_BWD, 10.0 * B * H * (double)N * N * hd, stream);
+  AvjProfScope prof(AVJ_FAM_ATTN_BWD, 10.0 * B * H * (double)N * N * hd, stream, B, N, H, hd);
   if (!force_simt_attn() && attn_bwd_use_umma() && avj_attention_umma_bwd_supported(dtype, hd))
     return avj_attention_bwd_umma(qkv, out, dout, lse, dqkv, ws, B, N, H, hd, scale, as_stream(stream));
   if (!force_simt_attn() && avj_attention_mma_supported(dtype, hd))

@@ -50,12 +50,15 @@ int avj_num_sms();
 enum { AVJ_FAM_GEMM = 0, AVJ_FAM_ATTN_FWD = 1, AVJ_FAM_ATTN_BWD = 2, AVJ_FAM_LN_FWD = 3, AVJ_FAM_LN_BWD = 4,
        AVJ_FAM_COLSUM = 5, AVJ_FAM_OPTIM = 6, AVJ_FAM_OTHER = 7, AVJ_FAM_COUNT = 8 };
 extern bool g_avj_prof_on;
-void avj_prof_begin(int family, double work, cudaStream_t s);
+void avj_prof_begin(int family, double work, cudaStream_t s, int d0 = 0, int d1 = 0, int d2 = 0, int d3 = 0);
 void avj_prof_end(cudaStream_t s);
 struct AvjProfScope {
   cudaStream_t s; bool on;
-  AvjProfScope(int family, double work, void* stream) : s(reinterpret_cast<cudaStream_t>(stream)), on(g_avj_prof_on) {
-    if (on) avj_prof_begin(family, work, s);
+  // d0..d3: free-form shape of the launch (GEMM: layout|epilogue bits, M, N, K; attention: B, N, H, hd;
+  // row kernels: rows, D) -- only written out by avj_prof_dump
+  AvjProfScope(int family, double work, void* stream, int d0 = 0, int d1 = 0, int d2 = 0, int d3 = 0)
+      : s(reinterpret_cast<cudaStream_t>(stream)), on(g_avj_prof_on) {
+    if (on) avj_prof_begin(family, work, s, d0, d1, d2, d3);
   }
   ~AvjProfScope() { if (on) avj_prof_end(s); }
 };

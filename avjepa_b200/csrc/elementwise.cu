@@ -76,6 +76,7 @@ extern "C" int avj_patchify(const float* x, const int64_t* idx, void* out, int o
   AVJ_CHECK(patch % 8 == 0 && W % 8 == 0, "avj_patchify: patch and W must be multiples of 8");
   AVJ_CHECK(T % tub == 0 && H % patch == 0 && W % patch == 0, "avj_patchify: dims not divisible by patch");
   if (B * K == 0) return 0;
+  AvjProfScope prof(AVJ_FAM_OTHER, (double)B * K * C * tub * patch * patch * (4 + (out_dtype == AVJ_BF16 ? 2 : 4)), stream, 1, B * K, C * tub * patch * patch);
   const int64_t total = (int64_t)B * K * (C * tub * patch * patch / 8);
   const int grid = grid_for(total, 256);
   if (out_dtype == AVJ_BF16)
@@ -119,6 +120,7 @@ extern "C" int avj_gather_rows_fwd(int dtype, const void* x, const int64_t* idx,
                                    int B, int N, int K, int D, void* stream) {
   AVJ_CHECK(D % 8 == 0, "avj_gather_rows_fwd: D must be a multiple of 8");
   if ((int64_t)B * K * D == 0) return 0;
+  AvjProfScope prof(AVJ_FAM_OTHER, (double)B * K * D * 2 * (dtype == AVJ_BF16 ? 2 : 4), stream, 2, B * K, D);
   const int grid = grid_for((int64_t)B * K * (D / 8), 256);
   if (dtype == AVJ_BF16)
     gather_rows_kernel<bf16, false><<<grid, 256, 0, as_stream(stream)>>>((const bf16*)x, idx, (bf16*)out, B, N, K, D);
@@ -132,6 +134,7 @@ extern "C" int avj_gather_rows_bwd(int dtype, const void* dout, const int64_t* i
                                    int B, int N, int K, int D, void* stream) {
   AVJ_CHECK(D % 8 == 0, "avj_gather_rows_bwd: D must be a multiple of 8");
   if ((int64_t)B * K * D == 0) return 0;
+  AvjProfScope prof(AVJ_FAM_OTHER, ((double)B * K + (double)B * N) * D * (dtype == AVJ_BF16 ? 2 : 4), stream, 3, B * K, D);
   const int grid = grid_for((int64_t)B * K * (D / 8), 256);
   if (dtype == AVJ_BF16)
     gather_rows_kernel<bf16, true><<<grid, 256, 0, as_stream(stream)>>>((const bf16*)dout, idx, (bf16*)dx, B, N, K, D);
@@ -171,6 +174,7 @@ extern "C" int avj_copy_rows(const void* in, int in_dtype, int ld_in, avj_rowmap
                              int rows, int D, int accumulate, void* stream) {
   AVJ_CHECK(D % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0, "avj_copy_rows: D/ld must be multiples of 8");
   if ((int64_t)rows * D == 0) return 0;
+  AvjProfScope prof(AVJ_FAM_OTHER, (double)rows * D * ((in_dtype == AVJ_BF16 ? 2 : 4) + (out_dtype == AVJ_BF16 ? 2 : 4) * (accumulate ? 2 : 1)), stream, 4, rows, D);
   const int grid = grid_for((int64_t)rows * (D / 8), 256);
   cudaStream_t s = as_stream(stream);
 #define LAUNCH(TI, TO) copy_rows_kernel<TI, TO><<<grid, 256, 0, s>>>((const TI*)in, ld_in, imap, (TO*)out, ld_out, omap, rows, D, accumulate)
@@ -204,6 +208,7 @@ extern "C" int avj_fill_mask_tokens(const float* mask_token, const float* pos, c
                                     float* x, int ld, avj_rowmap map, int rows, int D, void* stream) {
   AVJ_CHECK(D % 4 == 0, "avj_fill_mask_tokens: D must be a multiple of 4");
   if ((int64_t)rows * D == 0) return 0;
+  AvjProfScope prof(AVJ_FAM_OTHER, (double)rows * D * 8, stream, 5, rows, D);
   const int grid = grid_for((int64_t)rows * (D / 4), 256);
   fill_mask_tokens_kernel<<<grid, 256, 0, as_stream(stream)>>>(mask_token, pos, idx, x, ld, map, rows, D);
   AVJ_LAUNCH_CHECK();
@@ -277,7 +282,7 @@ extern "C" int avj_colsum(const void* in, int in_dtype, int ld, avj_rowmap map, 
                           int rows, int D, float* ws, void* stream) {
   AVJ_CHECK(D % 8 == 0 && ld % 8 == 0, "avj_colsum: D/ld must be multiples of 8");
   if (rows == 0 || D == 0) return 0;
-  AvjProfScope prof(AVJ_FAM_COLSUM, (double)rows * D * (in_dtype == AVJ_BF16 ? 2 : 4), stream);
+  AvjProfScope prof(AVJ_FAM_COLSUM, (double)rows * D * (in_dtype == AVJ_BF16 ? 2 : 4), stream, rows, D);
   const int gx = (D + 255) / 256;
   int ny = (4 * avj_num_sms() + gx - 1) / gx;                 // ~4 CTAs per SM
   if (ny > COLSUM_MAX_Y) ny = COLSUM_MAX_Y;
@@ -357,7 +362,7 @@ extern "C" int avj_colsum2(const void* in1, int ld1, int D1, float* out1, const 
   AVJ_CHECK(D1 % 8 == 0 && ld1 % 8 == 0 && D2 % 8 == 0 && ld2 % 8 == 0, "avj_colsum2: D/ld must be multiples of 8");
   AVJ_CHECK(out1 && out2 && ws, "avj_colsum2: NULL output/workspace");
   if (rows == 0) return 0;
-  AvjProfScope prof(AVJ_FAM_COLSUM, (double)rows * (D1 + D2) * (in_dtype == AVJ_BF16 ? 2 : 4), stream);
+  AvjProfScope prof(AVJ_FAM_COLSUM, (double)rows * (D1 + D2) * (in_dtype == AVJ_BF16 ? 2 : 4), stream, rows, D1, D2);
   const int gx1 = (D1 + 255) / 256, gx = gx1 + (D2 + 255) / 256;
   int ny = (4 * avj_num_sms() + gx - 1) / gx;
   if (ny > COLSUM_MAX_Y) ny = COLSUM_MAX_Y;
@@ -433,6 +438,7 @@ extern "C" int avj_loss_fwd_bwd(const float* z, const float* h, float* dz, float
                                 int64_t n, int n_masks, float loss_exp, int mode, float beta,
                                 float grad_scale, float* ws, void* stream) {
   AVJ_CHECK(n % 4 == 0 && n > 0, "avj_loss_fwd_bwd: n must be a positive multiple of 4");
+  AvjProfScope prof(AVJ_FAM_OTHER, (double)n * 12, stream, 6, (int)(n >> 10), 1024);
   const int nparts = (int)(avj_loss_ws_floats(n) - 1);
   const float denom = (mode == 1) ? 1.0f : loss_exp;
   // d/dz [ (1/(n*n_masks*p)) sum |d|^p ] : the kernel's g is d|d|^p/dd, so fold 1/(n*n_masks*p) here
@@ -623,6 +629,7 @@ __global__ void cast_kernel(const float* __restrict__ in, TOut* __restrict__ out
 
 extern "C" int avj_cast(const float* in, void* out, int out_dtype, int64_t n, void* stream) {
   if (n == 0) return 0;
+  AvjProfScope prof(AVJ_FAM_OTHER, (double)n * (4 + (out_dtype == AVJ_BF16 ? 2 : 4)), stream, 7, (int)(n >> 10), 1024);
   const int grid = grid_for(n / 8 + 1, 256);
   if (out_dtype == AVJ_BF16) cast_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>(in, (bf16*)out, n);
   else cast_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(in, (float*)out, n);
@@ -632,6 +639,7 @@ extern "C" int avj_cast(const float* in, void* out, int out_dtype, int64_t n, vo
 
 extern "C" int avj_memset_zero(void* ptr, int64_t nbytes, void* stream) {
   if (nbytes <= 0) return 0;
+  AvjProfScope prof(AVJ_FAM_OTHER, (double)nbytes, stream, 8, (int)(nbytes >> 10), 1024);
   AVJ_CUDA(cudaMemsetAsync(ptr, 0, (size_t)nbytes, as_stream(stream)));
   return 0;
 }

@@ -84,7 +84,7 @@ extern "C" int avj_layernorm_fwd(const float* x, const float* gamma, const float
                                  int rows, int D, float eps, void* stream) {
   AVJ_CHECK(D % 4 == 0 && D > 0, "avj_layernorm_fwd: D must be a positive multiple of 4");
   if (rows == 0) return 0;
-  AvjProfScope prof(AVJ_FAM_LN_FWD, (double)rows * D * (4 + (y_dtype == AVJ_BF16 ? 2 : 4)), stream);
+  AvjProfScope prof(AVJ_FAM_LN_FWD, (double)rows * D * (4 + (y_dtype == AVJ_BF16 ? 2 : 4)), stream, rows, D);
   if (y_dtype == AVJ_BF16) return launch_ln_fwd<bf16>(x, gamma, beta, (bf16*)y, mean, rstd, rows, D, eps, as_stream(stream));
   return launch_ln_fwd<float>(x, gamma, beta, (float*)y, mean, rstd, rows, D, eps, as_stream(stream));
 }
@@ -274,7 +274,7 @@ extern "C" int avj_layernorm_bwd(const void* dy, int dy_dtype, const float* x, c
   if (rows == 0) return 0;
   cudaStream_t s = as_stream(stream);
   AvjProfScope prof(AVJ_FAM_LN_BWD, (double)rows * D * ((dy_dtype == AVJ_BF16 ? 2 : 4) + 4 + (dres_in ? 4 : 0) + 4 +
-                                                         (dx_lp ? (lp_dtype == AVJ_BF16 ? 2 : 4) : 0)), stream);
+                                                         (dx_lp ? (lp_dtype == AVJ_BF16 ? 2 : 4) : 0)), stream, rows, D, dcolsum ? 1 : 0);
   if (dy_dtype == AVJ_BF16) {
     if (dx_lp && lp_dtype == AVJ_F32)
       return launch_ln_bwd<bf16, float>((const bf16*)dy, x, gamma, mean, rstd, dres_in, dx_out, (float*)dx_lp, dgamma, dbeta, dcolsum, ws, rows, D, s);

@@ -103,6 +103,19 @@ __device__ __forceinline__ void ua_stage(uint32_t tile, const bf16* __restrict__
   }
 }
 
+// One warp zeroes columns [hd, HDP) of a TMA-landed `rows` x HDP tile (generic-proxy stores: the caller
+// fences with fence.proxy.async before the tile is handed to the tensor core).
+template <int HDP>
+__device__ __forceinline__ void ua_zero_pad(uint32_t tile, int rows, int hd, int lane) {
+  constexpr int CH = HDP / 8;
+  const int c0 = hd / 8, npad = CH - c0;
+  for (int e = lane; e < rows * npad; e += 32) {
+    const int r = e / npad, c = c0 + e % npad;
+    const uint32_t dst = tile + r * UaTile<HDP>::PITCH + (UaTile<HDP>::chunk(r, c) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+  }
+}
+
 // Register re-partitioning between warpgroups (warps 4k..4k+3 must all execute the same one).
 template <int R> __device__ __forceinline__ void ua_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 template <int R> __device__ __forceinline__ void ua_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }

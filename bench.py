@@ -201,6 +201,7 @@ def main():
     ap.add_argument('--cpu-sample-batch', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--fp32', action='store_true', help='fp32 check mode instead of bf16')
+    ap.add_argument('--prof-dump', default=None, help='write the per-launch timing CSV of the instrumented step here')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -300,6 +301,8 @@ def main():
         step(host_clips.to(dev), host_asgram.to(dev), *to_device(host_masks[-1]), epoch=0, sync=True)
         torch.cuda.synchronize()
         fam = _cabi.prof_collect()
+        if args.prof_dump:
+            _cabi.prof_dump(args.prof_dump)
         _cabi.prof_enable(False)
         g_ms, g_fl, g_n = fam['gemm']
         achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0

@@ -190,9 +190,13 @@ int avj_memset_zero(void* ptr, int64_t nbytes, void* stream);
 /* ---- in-library kernel timing (measurement only): while enabled, every GEMM / attention / LayerNorm /
  *      column-sum / optimizer entry point brackets its launches with CUDA events on its stream.
  *      avj_prof_collect sums one family: 0 gemm (work = FLOPs), 1 attention fwd, 2 attention bwd (FLOPs),
- *      3 layernorm fwd, 4 layernorm bwd, 5 colsum, 6 optimizer (work = algorithmic bytes). */
+ *      3 layernorm fwd, 4 layernorm bwd, 5 colsum, 6 optimizer, 7 other row kernels (work = algorithmic bytes). */
 int avj_prof_enable(int on);
 int avj_prof_collect(int family, double* ms, double* work, int* launches);
+/* one CSV line per timed launch, in launch order: family,work,ms,d0,d1,d2,d3 (d* = the launch's shape:
+ * GEMM layout|epilogue bits,M,N,K; attention B,N,H,hd; row kernels rows,D; family 7 = gather/copy/loss/...
+ * with d0 = 1 patchify, 2/3 gather fwd/bwd, 4 copy_rows, 5 mask-token fill, 6 loss, 7 cast, 8 memset). */
+int avj_prof_dump(const char* path);
 
 /* ---- whole-stack schedules: L pre-LN transformer blocks (Block.forward / Attention.forward /
  *      MLP.forward, src/models/utils/modules.py:114-120, :61-78, :30-36) issued as ONE call, so the

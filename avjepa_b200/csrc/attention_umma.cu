@@ -23,6 +23,7 @@
 
 #include "umma_attn.cuh"
 #include <mutex>
+#include <type_traits>
 #include <stdlib.h>
 #include <utility>
 #include <vector>
@@ -190,7 +191,11 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
     const uint32_t t_s = tmem + ((uint32_t)(q * 32) << 16);
     const uint32_t t_o = t_s + UA_O_COL;
     float m = -INFINITY, l = 0.f;
-    for (int t = 0; t < T; ++t) {
+    // MASKED is a compile-time tag: only the LAST key tile of a sequence with N % 128 != 0 carries the
+    // 128 compare+select pairs that push keys past N to -inf (as a run-time predicate the compiler
+    // if-converts them into every tile: +2 instructions per score in an issue/MUFU-bound loop)
+    auto tile = [&](const int t, auto masked_tag) {
+      constexpr bool MASKED = decltype(masked_tag)::value;
       ua_mbar_wait(s_full, t & 1);
       ua_fence_after();
       float s[128];
@@ -198,8 +203,8 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
       ua_ld_wait();
       ua_fence_before();
       ua_mbar_arrive(s_free);
-      const int nvalid = N - t * UA_BN;
-      if (nvalid < UA_BN) {
+      if constexpr (MASKED) {
+        const int nvalid = N - t * UA_BN;
 #pragma unroll
         for (int j = 0; j < 128; ++j) if (j >= nvalid) s[j] = -INFINITY;
       }
@@ -245,7 +250,10 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
       ua_fence_async_smem();
       ua_fence_before();
       ua_mbar_arrive(p_full);
-    }
+    };
+    const bool tail = (N % UA_BN) != 0;
+    for (int t = 0; t + 1 < T; ++t) tile(t, std::false_type{});
+    if (tail) tile(T - 1, std::true_type{}); else tile(T - 1, std::false_type{});
     ua_mbar_wait(o_done, (T - 1) & 1);
     ua_fence_after();
     const int qi = q0 + row;
@@ -352,8 +360,10 @@ static int ua_launch(const bf16* qkv, bf16* out, float* lse, int B, int N, int H
 int avj_attention_fwd_umma(const void* qkv, void* out, float* lse, int B, int N, int H, int hd, float scale, cudaStream_t s) {
   static int use_tma = -1;
   if (use_tma < 0) { const char* e = getenv("AVJ_ATTN_TMA"); use_tma = (e && e[0] == '0') ? 0 : 1; }
+  static int use_tma32 = -1;   // AVJ_ATTN_TMA32=0: head_dim <= 32 goes back to the cp.async gather loaders
+  if (use_tma32 < 0) { const char* e = getenv("AVJ_ATTN_TMA32"); use_tma32 = (e && e[0] == '0') ? 0 : use_tma; }
   if (hd <= 32) {
-    if (use_tma && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0)
+    if (use_tma32 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0)
       return ua_launch<32, true>((const bf16*)qkv, (bf16*)out, lse, B, N, H, hd, scale, s);
     return ua_launch<32, false>((const bf16*)qkv, (bf16*)out, lse, B, N, H, hd, scale, s);
   }

@@ -381,9 +381,11 @@ int avj_attention_bwd_umma(const void* qkv, const void* out, const void* dout, c
   if (rc) return rc;
   static int use_tma = -1;
   if (use_tma < 0) { const char* e = getenv("AVJ_ATTN_TMA"); use_tma = (e && e[0] == '0') ? 0 : 1; }
+  static int use_tma32 = -1;   // AVJ_ATTN_TMA32=0: head_dim <= 32 goes back to the cp.async gather loaders
+  if (use_tma32 < 0) { const char* e = getenv("AVJ_ATTN_TMA32"); use_tma32 = (e && e[0] == '0') ? 0 : use_tma; }
   const bool aligned = ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(dout)) & 15) == 0;
   if (hd <= 32) {
-    if (use_tma && aligned)
+    if (use_tma32 && aligned)
       return ub_both<32, true>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, B, N, n_pad, H, hd, scale, s);
     return ub_both<32, false>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, B, N, n_pad, H, hd, scale, s);
   }

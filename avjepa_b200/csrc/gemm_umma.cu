@@ -42,6 +42,7 @@ struct UmmaParams {
   int a_mn_major, b_mn_major;
   uint32_t mn_lbo, mn_sbo, mn_kadv;   // MN-major descriptor fields / k-advance (16 B units)
   void* C;
+  int tma_store;         // thread==row epilogues: bf16 C (and pre_out) leave through smem + TMA bulk stores
   avj_epilogue ep;
 };
 
@@ -79,6 +80,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// TMA store of one 32-row x 32-column bf16 block (SWIZZLE_64B staging tile) at {column c0, row c1}; rows and
+// columns past the tensor bounds are clipped by the hardware.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -146,8 +159,9 @@ __device__ __forceinline__ void sts_f4(uint32_t a, float4 v) {
 
 // One accumulator tile (this warp's 32 rows x [c_lo, c_hi) columns) through the fused epilogue.
 // `wait_full` blocks until the tile's MMAs have retired, `release` signals that the TMEM buffer is drained.
-template <int EPI, class WaitFull, class Release>
-__device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int row_base, int n_blk, uint32_t taddr, uint32_t stg,
+template <int EPI, int NBUF, bool TS, class WaitFull, class Release>
+__device__ __forceinline__ void epilogue_tile(const UmmaParams& p, const CUtensorMap* tma_c, const CUtensorMap* tma_p,
+                                              int row_base, int n_blk, uint32_t taddr, uint32_t stg,
                                               int lane, int c_lo, int c_hi, WaitFull wait_full, Release release) {
   const avj_epilogue& ep = p.ep;
   const int cols_half = c_hi - c_lo;
@@ -156,9 +170,11 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int row_base,
 
   if (EPI == EPI_PLAIN || EPI == EPI_GELU || EPI == EPI_DACT) {
     // ---------------- direct: thread == row, 32 consecutive columns per step ----------------
-    // the warp's bias segment goes to shared memory once per tile (broadcast reads afterwards)
     const bool has_bias = (EPI != EPI_DACT) && ep.bias != nullptr;
-    if (has_bias) {
+    constexpr bool ts = TS;
+    // direct stores: the warp's bias segment goes to shared memory once per tile (broadcast reads afterwards);
+    // TMA stores own the staging buffer, so there the bias comes straight from L1 (one address per warp)
+    if (has_bias && !ts) {
       __syncwarp();                               // every lane is done with the previous tile's bias
       if (lane * 4 < cols_half) sts_f4(stg + lane * 16, ld_f4(ep.bias + n_blk * p.block_n + c_lo + lane * 4));
       __syncwarp();
@@ -166,6 +182,24 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int row_base,
     const int64_t row = row_base + lane;
     const bool row_ok = row < p.M;
     const int64_t prow = row_ok ? map_row(ep.out_map, row) : 0;
+    // TMA-store staging: NBUF tiles of 32 rows x 64 B (SWIZZLE_64B: 16-byte chunk j of row r sits at j ^ ((r >> 1) & 3))
+    const uint32_t st_row = stg + lane * 64;
+    const int st_swz = (lane >> 1) & 3;
+    int st_buf = 0;
+    auto stage_store = [&](const CUtensorMap* map, const float (&v)[32], int n0) {
+      if (lane == 0) tma_store_wait_read<NBUF - 1>();          // the tile written NBUF stores ago has been read
+      __syncwarp();
+      const uint32_t dst = st_row + st_buf * 2048;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((j ^ st_swz) << 4)),
+                     "r"(pack_bf16x2(v[8 * j], v[8 * j + 1])), "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])),
+                     "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])), "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7])) : "memory");
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tma_store_2d(map, stg + st_buf * 2048, n0, row_base);
+      st_buf = (st_buf + 1) % NBUF;
+    };
     wait_full();
     tmem_ld32_issue(taddr + c_lo, raw);
     for (int c = c_lo; c < c_hi; c += 32) {
@@ -188,18 +222,22 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int row_base,
       if (has_bias) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 b = lds_f4(stg + (c - c_lo + j * 4) * 4);
+          const float4 b = ts ? __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + j) : lds_f4(stg + (c - c_lo + j * 4) * 4);
           v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
         }
       }
-      if (!row_ok) continue;
+      if (!ts && !row_ok) continue;
       if (EPI == EPI_GELU) {
         if (ep.pre_out) {
-          uint4* pp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.pre_out) + row * (int64_t)p.N + n0);
+          if (ts) {
+            stage_store(tma_p, v, n0);
+          } else {
+            uint4* pp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.pre_out) + row * (int64_t)p.N + n0);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            pp[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                               pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+            for (int j = 0; j < 4; ++j)
+              pp[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                 pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+          }
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = gelu_fwd<true>(v[i]);
@@ -217,7 +255,9 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int row_base,
           }
         }
       }
-      if (ep.out_dtype == AVJ_F32) {
+      if (ts) {
+        stage_store(tma_c, v, n0);
+      } else if (ep.out_dtype == AVJ_F32) {
         float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + prow * (int64_t)p.ldc + n0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -339,21 +379,22 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, int row_base,
 // EW = number of epilogue warps: 8 (two per TMEM lane quarter, half of the columns each) or 16 (four per
 // quarter, a quarter of the columns each) for the thread==row epilogues, which are latency- rather than
 // issue-bound and double their throughput with twice the warps in flight.
-template <int EPI, int EW>
+template <int EPI, int EW, bool TS>
 __global__ void __launch_bounds__(128 + 32 * EW, 1)
-gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const UmmaParams p) {
+gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_p, const UmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t smem_a = base;
   const uint32_t smem_b = base + UG_STAGES * UG_A_STAGE_BYTES;
-  const uint32_t bars = smem_b + UG_STAGES * UG_B_STAGE_BYTES;
+  const uint32_t epi_stage = smem_b + UG_STAGES * UG_B_STAGE_BYTES;   // [UG_EPI_WARPS] x 4 KB, 1024-byte aligned
+  const uint32_t bars = epi_stage + UG_EPI_WARPS * UG_EPI_STAGE_BYTES;
   const uint32_t full_bar = bars;                       // [UG_STAGES]
   const uint32_t empty_bar = bars + 8 * UG_STAGES;      // [UG_STAGES]
   const uint32_t tfull_bar = bars + 16 * UG_STAGES;     // [2]
   const uint32_t tempty_bar = tfull_bar + 16;           // [2]
   const uint32_t tmem_slot = tempty_bar + 16;           // u32
-  const uint32_t epi_stage = bars + 256;                // [UG_EPI_WARPS] x 4 KB: bias row / transpose buffer
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -450,7 +491,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   } else {
     // ================= epilogue warpgroups (EW warps) =================
     // EW/4 warps per TMEM lane quarter, each taking BN/(EW/4) of the tile's columns, 32 columns at a time.
-    reg_inc<EW == 8 ? 232 : 112>();
+    reg_inc<EW == 8 ? 232 : 104>();   // pool: 640 x 96 at launch; 128 x (96 - 40) freed >= 512 x (104 - 96) claimed (112 would deadlock)
     const int q = warp & 3;                          // TMEM lane quarter this warp may touch
     const int ew = warp - 4;
     const int part = ew >> 2;
@@ -463,11 +504,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
       const int row_base = m_blk * UG_BM + q * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * UG_MAX_BN;
-      epilogue_tile<EPI>(p, row_base, n_blk, taddr, stg, lane, c_lo, c_hi,
+      epilogue_tile<EPI, 16 / EW, TS>(p, &tma_c, &tma_p, row_base, n_blk, taddr, stg, lane, c_lo, c_hi,
                          [&] { mbar_wait(tfull_bar + 8 * acc, acc_phase); tc_fence_after(); },
                          [&] { tc_fence_before(); mbar_arrive(tempty_bar + 8 * acc); });
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (TS && lane == 0) tma_store_wait_read<0>();   // staging smem must outlive the bulk stores' reads
   }
 
   tc_fence_before();
@@ -532,21 +574,22 @@ __device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
-template <int EPI, int EW>
+template <int EPI, int EW, bool TS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
-gemm_umma2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const UmmaParams p) {
+gemm_umma2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                  const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_p, const UmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t smem_a = base;
   const uint32_t smem_b = base + UG2_STAGES * UG2_STAGE_BYTES;
-  const uint32_t bars = smem_b + UG2_STAGES * UG2_STAGE_BYTES;
+  const uint32_t epi_stage = smem_b + UG2_STAGES * UG2_STAGE_BYTES;   // 1024-byte aligned
+  const uint32_t bars = epi_stage + UG_EPI_WARPS * UG_EPI_STAGE_BYTES;
   const uint32_t full_bar = bars;                       // [UG2_STAGES]  (used in the leader only)
   const uint32_t empty_bar = bars + 8 * UG2_STAGES;     // [UG2_STAGES]
   const uint32_t tfull_bar = bars + 16 * UG2_STAGES;    // [2]
   const uint32_t tempty_bar = tfull_bar + 16;           // [2]           (used in the leader only)
   const uint32_t tmem_slot = tempty_bar + 16;           // u32
-  const uint32_t epi_stage = bars + 256;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -647,7 +690,7 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     }
   } else {
     // ================= epilogue warpgroups (both CTAs, own 128 accumulator rows) =================
-    reg_inc<EW == 8 ? 232 : 112>();
+    reg_inc<EW == 8 ? 232 : 104>();   // pool: 640 x 96 at launch; 128 x (96 - 40) freed >= 512 x (104 - 96) claimed (112 would deadlock)
     const int q = warp & 3;
     const int ew = warp - 4;
     const int part = ew >> 2;
@@ -661,11 +704,12 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       const int row_base = m_blk * 2 * UG_BM + (int)rank * UG_BM + q * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * UG_MAX_BN;
       const uint32_t leader_tempty = mapa_u32(tempty_bar + 8 * acc, 0);
-      epilogue_tile<EPI>(p, row_base, n_blk, taddr, stg, lane, c_lo, c_hi,
+      epilogue_tile<EPI, 16 / EW, TS>(p, &tma_c, &tma_p, row_base, n_blk, taddr, stg, lane, c_lo, c_hi,
                          [&] { mbar_wait(tfull_bar + 8 * acc, acc_phase); tc_fence_after(); },
                          [&] { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive_cluster(leader_tempty); });
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (TS && lane == 0) tma_store_wait_read<0>();
   }
 
   tc_fence_before();
@@ -697,26 +741,28 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 struct MapKey {
-  const void* ptr; uint64_t inner, outer, ld; uint32_t box_inner, box_outer;
+  const void* ptr; uint64_t inner, outer, ld; uint32_t box_inner, box_outer, swz64;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer;
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer &&
+           swz64 == o.swz64;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = reinterpret_cast<size_t>(k.ptr);
     h = h * 1000003u ^ k.inner; h = h * 1000003u ^ k.outer; h = h * 1000003u ^ k.ld;
-    h = h * 1000003u ^ k.box_inner; h = h * 1000003u ^ k.box_outer;
+    h = h * 1000003u ^ k.box_inner; h = h * 1000003u ^ k.box_outer; h = h * 1000003u ^ k.swz64;
     return h;
   }
 };
 
 // 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows, row pitch `ld` elements.
+// swz64: SWIZZLE_64B (32-element rows of the epilogue's store tiles) instead of SWIZZLE_128B.
 static int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
-                          uint32_t box_outer, CUtensorMap* out) {
+                          uint32_t box_outer, CUtensorMap* out, uint32_t swz64 = 0) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
+  MapKey key{ptr, inner, outer, ld, box_inner, box_outer, swz64};
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
@@ -729,8 +775,8 @@ static int get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint6
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   AVJ_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%llu outer=%llu ld=%llu box=%ux%u", (int)r,
             ptr, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner, box_outer);
   {
@@ -831,28 +877,55 @@ int avj_gemm_umma(int layout, const void* A, const void* B, void* C, int M, int 
   else if (ep.dact_aux) epi = EPI_DACT;
   else epi = EPI_PLAIN;
 
+  // thread==row epilogues with a plain [M, N] bf16 C: 32 x 32 blocks leave through shared memory and TMA bulk
+  // stores (full 64-byte row segments instead of 32 scattered 16-byte pieces per warp instruction)
+  static const uint32_t use_ts = env_u32("AVJ_GEMM_TMA_STORE", 1);
+  CUtensorMap mc, mp;
+  memset(&mc, 0, sizeof(mc)); memset(&mp, 0, sizeof(mp));
+  p.tma_store = 0;
+  if (use_ts && epi <= EPI_DACT && ep.out_dtype == AVJ_BF16 && ep.out_map.rows_per_group == 0 && ep.out_map.row_offset == 0 &&
+      ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
+      (!ep.pre_out || (reinterpret_cast<uintptr_t>(ep.pre_out) & 15) == 0)) {
+    rc = get_tensor_map(C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, 32, &mc, 1);
+    if (rc) return rc;
+    if (epi == EPI_GELU && ep.pre_out) {
+      rc = get_tensor_map(ep.pre_out, (uint64_t)N, (uint64_t)M, (uint64_t)N, 32, 32, &mp, 1);
+      if (rc) return rc;
+    }
+    p.tma_store = 1;
+  }
+
   // thread==row epilogues run 16 epilogue warps when the tile splits into four 32-column-aligned parts
   static const uint32_t ew16 = env_u32("AVJ_GEMM_EW16", 1);
   const bool wide = ew16 && epi <= EPI_DACT && p.block_n % 128 == 0;
 
-  typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const UmmaParams);
-  // [two][wide][epi]
+  typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const UmmaParams);
+  // [two][wide][epi], then the TMA-store variants of the three thread==row epilogues: [two][wide][epi]
   static const kern_t kerns[2][2][5] = {
-      {{gemm_umma_kernel<EPI_PLAIN, 8>, gemm_umma_kernel<EPI_GELU, 8>, gemm_umma_kernel<EPI_DACT, 8>,
-        gemm_umma_kernel<EPI_TRANSPOSED, 8>, gemm_umma_kernel<EPI_GENERIC, 8>},
-       {gemm_umma_kernel<EPI_PLAIN, 16>, gemm_umma_kernel<EPI_GELU, 16>, gemm_umma_kernel<EPI_DACT, 16>, nullptr, nullptr}},
-      {{gemm_umma2_kernel<EPI_PLAIN, 8>, gemm_umma2_kernel<EPI_GELU, 8>, gemm_umma2_kernel<EPI_DACT, 8>,
-        gemm_umma2_kernel<EPI_TRANSPOSED, 8>, gemm_umma2_kernel<EPI_GENERIC, 8>},
-       {gemm_umma2_kernel<EPI_PLAIN, 16>, gemm_umma2_kernel<EPI_GELU, 16>, gemm_umma2_kernel<EPI_DACT, 16>, nullptr, nullptr}}};
+      {{gemm_umma_kernel<EPI_PLAIN, 8, false>, gemm_umma_kernel<EPI_GELU, 8, false>, gemm_umma_kernel<EPI_DACT, 8, false>,
+        gemm_umma_kernel<EPI_TRANSPOSED, 8, false>, gemm_umma_kernel<EPI_GENERIC, 8, false>},
+       {gemm_umma_kernel<EPI_PLAIN, 16, false>, gemm_umma_kernel<EPI_GELU, 16, false>, gemm_umma_kernel<EPI_DACT, 16, false>, nullptr, nullptr}},
+      {{gemm_umma2_kernel<EPI_PLAIN, 8, false>, gemm_umma2_kernel<EPI_GELU, 8, false>, gemm_umma2_kernel<EPI_DACT, 8, false>,
+        gemm_umma2_kernel<EPI_TRANSPOSED, 8, false>, gemm_umma2_kernel<EPI_GENERIC, 8, false>},
+       {gemm_umma2_kernel<EPI_PLAIN, 16, false>, gemm_umma2_kernel<EPI_GELU, 16, false>, gemm_umma2_kernel<EPI_DACT, 16, false>, nullptr, nullptr}}};
+  static const kern_t kerns_ts[2][2][3] = {
+      {{gemm_umma_kernel<EPI_PLAIN, 8, true>, gemm_umma_kernel<EPI_GELU, 8, true>, gemm_umma_kernel<EPI_DACT, 8, true>},
+       {gemm_umma_kernel<EPI_PLAIN, 16, true>, gemm_umma_kernel<EPI_GELU, 16, true>, gemm_umma_kernel<EPI_DACT, 16, true>}},
+      {{gemm_umma2_kernel<EPI_PLAIN, 8, true>, gemm_umma2_kernel<EPI_GELU, 8, true>, gemm_umma2_kernel<EPI_DACT, 8, true>},
+       {gemm_umma2_kernel<EPI_PLAIN, 16, true>, gemm_umma2_kernel<EPI_GELU, 16, true>, gemm_umma2_kernel<EPI_DACT, 16, true>}}};
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
     for (int t = 0; t < 2; ++t)
       for (int w = 0; w < 2; ++w)
         for (int i = 0; i < 5 && attr_err == cudaSuccess; ++i)
-          if (kerns[t][w][i])
+          if (kerns[t][w][i]) {
             attr_err = cudaFuncSetAttribute(kerns[t][w][i], cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             t == 0 ? UG_SMEM_BYTES : UG2_SMEM_BYTES);
+            if (i < 3 && attr_err == cudaSuccess)
+              attr_err = cudaFuncSetAttribute(kerns_ts[t][w][i], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              t == 0 ? UG_SMEM_BYTES : UG2_SMEM_BYTES);
+          }
   });
   AVJ_CHECK(attr_err == cudaSuccess, "cudaFuncSetAttribute(gemm_umma_kernel) failed: %s", cudaGetErrorString(attr_err));
 
@@ -860,10 +933,10 @@ int avj_gemm_umma(int layout, const void* A, const void* B, void* C, int M, int 
   const int threads = 128 + 32 * (wide ? 16 : 8);
   if (two) {
     const int clusters = units < workers ? units : workers;
-    kerns[1][wide][epi]<<<2 * clusters, threads, UG2_SMEM_BYTES, s>>>(ma, mb, p);
+    (p.tma_store ? kerns_ts[1][wide][epi] : kerns[1][wide][epi])<<<2 * clusters, threads, UG2_SMEM_BYTES, s>>>(ma, mb, mc, mp, p);
   } else {
     const int grid = units < sms ? units : sms;
-    kerns[0][wide][epi]<<<grid, threads, UG_SMEM_BYTES, s>>>(ma, mb, p);
+    (p.tma_store ? kerns_ts[0][wide][epi] : kerns[0][wide][epi])<<<grid, threads, UG_SMEM_BYTES, s>>>(ma, mb, mc, mp, p);
   }
   AVJ_LAUNCH_CHECK();
   return 0;

@@ -47,7 +47,8 @@ template <int HDP> struct UaSmem {
 
 // TMA = true (hd == 64): one elected thread issues 16 KB box loads (rows past N are zero-filled by
 // the hardware); TMA = false: the loader warp gathers 16-byte chunks with cp.async and pads in smem.
-template <int HDP, bool TMA>
+// POLY: every fourth pair of scores takes ua_exp2_poly (FMA pipe) instead of MUFU ex2.
+template <int HDP, bool TMA, bool POLY>
 __global__ void __launch_bounds__(UA_THREADS, 2)
 fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restrict__ qkv, bf16* __restrict__ out,
                    float* __restrict__ lse, int N, int H, int hd, float scale_log2) {
@@ -221,8 +222,10 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
       uint32_t pk[64];
 #pragma unroll
       for (int j = 0; j < 128; j += 2) {
-        const float p0 = ua_exp2(fmaf(s[j], scale_log2, -mb));
-        const float p1 = ua_exp2(fmaf(s[j + 1], scale_log2, -mb));
+        const float x0 = fmaf(s[j], scale_log2, -mb), x1 = fmaf(s[j + 1], scale_log2, -mb);
+        const bool poly = POLY && ((j >> 1) & 3) == 3;
+        const float p0 = poly ? ua_exp2_poly(x0) : ua_exp2(x0);
+        const float p1 = poly ? ua_exp2_poly(x1) : ua_exp2(x1);
         rsum += p0 + p1;
         pk[j >> 1] = pack_bf16x2(p0, p1);
       }
@@ -335,14 +338,14 @@ int ua_make_map3d(const void* qkv, int B, int N, int cols, int box_rows, CUtenso
   return 0;
 }
 
-template <int HDP, bool TMA>
+template <int HDP, bool TMA, bool POLY>
 static int ua_launch(const bf16* qkv, bf16* out, float* lse, int B, int N, int H, int hd, float scale, cudaStream_t s) {
   static bool set = false;
   if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(fa_fwd_umma_kernel<HDP, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UaSmem<HDP>::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(fa_fwd_umma_kernel<HDP, TMA, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UaSmem<HDP>::TOTAL);
     AVJ_CHECK(e == cudaSuccess, "cudaFuncSetAttribute(fa_fwd_umma_kernel) failed: %s", cudaGetErrorString(e));
     // two CTAs per SM need the full 228 KB shared-memory carve-out
-    cudaFuncSetAttribute(fa_fwd_umma_kernel<HDP, TMA>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(fa_fwd_umma_kernel<HDP, TMA, POLY>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     set = true;
   }
   CUtensorMap map;
@@ -352,7 +355,7 @@ static int ua_launch(const bf16* qkv, bf16* out, float* lse, int B, int N, int H
     if (rc) return rc;
   }
   dim3 grid((N + UA_BM - 1) / UA_BM, H, B);
-  fa_fwd_umma_kernel<HDP, TMA><<<grid, UA_THREADS, UaSmem<HDP>::TOTAL, s>>>(map, qkv, out, lse, N, H, hd, scale * 1.4426950408889634f);
+  fa_fwd_umma_kernel<HDP, TMA, POLY><<<grid, UA_THREADS, UaSmem<HDP>::TOTAL, s>>>(map, qkv, out, lse, N, H, hd, scale * 1.4426950408889634f);
   AVJ_LAUNCH_CHECK();
   return 0;
 }
@@ -362,12 +365,17 @@ int avj_attention_fwd_umma(const void* qkv, void* out, float* lse, int B, int N,
   if (use_tma < 0) { const char* e = getenv("AVJ_ATTN_TMA"); use_tma = (e && e[0] == '0') ? 0 : 1; }
   static int use_tma32 = -1;   // AVJ_ATTN_TMA32=0: head_dim <= 32 goes back to the cp.async gather loaders
   if (use_tma32 < 0) { const char* e = getenv("AVJ_ATTN_TMA32"); use_tma32 = (e && e[0] == '0') ? 0 : use_tma; }
+  static int use_poly = -1;    // AVJ_ATTN_POLY=1: a quarter of the exp2 evaluations on the FMA pipe
+  if (use_poly < 0) { const char* e = getenv("AVJ_ATTN_POLY"); use_poly = (e && e[0] == '1') ? 1 : 0; }
+  const bool al = (reinterpret_cast<uintptr_t>(qkv) & 15) == 0;
+#define UA_GO(HDP_, TMA_) \
+  return use_poly ? ua_launch<HDP_, TMA_, true>((const bf16*)qkv, (bf16*)out, lse, B, N, H, hd, scale, s) \
+                  : ua_launch<HDP_, TMA_, false>((const bf16*)qkv, (bf16*)out, lse, B, N, H, hd, scale, s)
   if (hd <= 32) {
-    if (use_tma32 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0)
-      return ua_launch<32, true>((const bf16*)qkv, (bf16*)out, lse, B, N, H, hd, scale, s);
-    return ua_launch<32, false>((const bf16*)qkv, (bf16*)out, lse, B, N, H, hd, scale, s);
+    if (use_tma32 && al) { UA_GO(32, true); }
+    UA_GO(32, false);
   }
-  if (hd == 64 && use_tma && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0)
-    return ua_launch<64, true>((const bf16*)qkv, (bf16*)out, lse, B, N, H, hd, scale, s);
-  return ua_launch<64, false>((const bf16*)qkv, (bf16*)out, lse, B, N, H, hd, scale, s);
+  if (hd == 64 && use_tma && al) { UA_GO(64, true); }
+  UA_GO(64, false);
+#undef UA_GO
 }

@@ -126,6 +126,19 @@ __device__ __forceinline__ float ua_exp2(float x) {
   return y;
 }
 
+// exp2 on the FMA pipe (Cody-Waite split + degree-3 minimax of 2^r on [-0.5, 0.5], max relative error 7.5e-5,
+// far below the bf16 rounding of P): 8 FMA-pipe instructions.  The softmax loops route a fixed fraction of their
+// elements here because the 16 exp2/clk/SM MUFU units, not the tensor pipe, bound attention at head_dim <= 64.
+__device__ __forceinline__ float ua_exp2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;                       // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float r = x - (t - 12582912.0f);
+  float p = fmaf(0.0551716685f, r, 0.2426111251f);
+  p = fmaf(p, r, 0.6932609677f);
+  p = fmaf(p, r, 0.9999280572f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 // 3-D TMA load of one 128-row x 64-col bf16 box of the qkv tensor viewed as {3*H*hd, N, B}
 __device__ __forceinline__ void ua_tma3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(

@@ -54,10 +54,14 @@
 // fit next to a second CTA; at hd = 64 there is room for 3 (112 KB per CTA in the dK/dV pass).
 template <int HDP, bool KV> struct UbSmem {
   static constexpr int NST = HDP == 32 ? 4 : 3;
+  // column-statistics buffers of the KV pass: two (one named barrier per step) where shared memory allows;
+  // at hd = 64 two co-resident CTAs leave room for one (two barriers per step)
+  static constexpr int SB = HDP == 32 ? 2 : 1;
   static constexpr uint32_t ROW_TILE = 128 * UaTile<HDP>::PITCH, COL_TILE = 64 * UaTile<HDP>::PITCH;
   static constexpr uint32_t R1 = 0, R2 = ROW_TILE, C1 = 2 * ROW_TILE, C2 = C1 + NST * COL_TILE,
                             DS = C2 + NST * COL_TILE, P = DS + UB_PD_TILE,
-                            BARS = KV ? P + UB_PD_TILE : P, TOTAL = BARS + 128;
+                            STAT = KV ? P + UB_PD_TILE : P,            // KV pass: [SB][lse2 64 | delta 64] floats
+                            BARS = STAT + (KV ? SB * 512 : 0), TOTAL = BARS + 128;
 };
 
 template <int HDP, bool TMA, bool KV>
@@ -234,6 +238,9 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
     const int ri = r0 + row;
     float my_l2 = 0.f, my_dl = 0.f;
     if (!KV && ri < N) { my_l2 = lse_bh[ri]; my_dl = delta_bh[ri]; }
+    float* stat = reinterpret_cast<float*>(ub_raw + L::STAT);
+    float my_stat = 0.f;
+    if (KV) my_stat = __ldg((row < 64 ? lse_bh : delta_bh - 64) + row);   // tile 0 (rows are padded to n_pad with zeros)
     for (int t = 0; t < T; ++t) {
       ua_mbar_wait(t_full, t & 1);
       ua_fence_after();
@@ -244,20 +251,24 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
       ua_fence_before();
       ua_mbar_arrive(t_free);
       uint32_t pk_p[KV ? 32 : 1], pk_d[32];
-      // per-column statistics of this query tile straight from global memory: every thread of the CTA reads
-      // the same 2 x 256 bytes (L1 broadcast); the next tile's lines are prefetched while this one computes
-      const float* st_l2 = lse_bh + t * UB_BN;
-      const float* st_dl = delta_bh + t * UB_BN;
-      if (KV && t + 1 < T && lane < 4) {
-        const float* pf = (lane < 2 ? st_l2 : st_dl) + UB_BN + (lane & 1) * 32;
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+      // per-column statistics of this query tile: thread i publishes ONE value (i < 64: lse2 of column i,
+      // else delta of column i - 64) that it loaded a whole step earlier, so no thread ever waits on global
+      // memory; everybody then reads the 2 x 256 bytes as shared-memory broadcasts
+      if constexpr (KV) {
+        float* sb = stat + (t % L::SB) * 128;
+        if (L::SB == 1) asm volatile("bar.sync 1, 128;" ::: "memory");     // previous tile's readers are done
+        sb[row] = my_stat;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (t + 1 < T) my_stat = __ldg((row < 64 ? lse_bh : delta_bh - 64) + (t + 1) * UB_BN + row);
       }
+      const float* st_l2 = stat + (KV ? (t % L::SB) * 128 : 0);
+      const float* st_dl = st_l2 + 64;
 #pragma unroll
       for (int j = 0; j < 64; j += 4) {
         float l2[4], dl[4];
         if constexpr (KV) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(st_l2 + j));
-          const float4 d = __ldg(reinterpret_cast<const float4*>(st_dl + j));
+          const float4 a = *reinterpret_cast<const float4*>(st_l2 + j);
+          const float4 d = *reinterpret_cast<const float4*>(st_dl + j);
           l2[0] = a.x; l2[1] = a.y; l2[2] = a.z; l2[3] = a.w;
           dl[0] = d.x; dl[1] = d.y; dl[2] = d.z; dl[3] = d.w;
         } else {

@@ -201,6 +201,8 @@ def main():
     ap.add_argument('--cpu-sample-batch', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--fp32', action='store_true', help='fp32 check mode instead of bf16')
+    ap.add_argument('--profile-only', action='store_true',
+                    help='run warm-up + timed steps of the resident loop and exit (driver for ncu launch lists; prints no bench line)')
     ap.add_argument('--prof-dump', default=None, help='write the per-launch timing CSV of the instrumented step here')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
@@ -282,6 +284,10 @@ def main():
     sampler.start()
     ms_res, flops_clip, launches, loss_res = timed_loop(0, e2e=False)
     clocks = sampler.stop()
+    if args.profile_only:
+        if rank == 0:
+            print(json.dumps(dict(profile_only=True, ms_per_step=ms_res, gpu_launches=int(launches))), flush=True)
+        return
     ms_e2e, _, _, loss_e2e = timed_loop(K + W, e2e=True)
 
     # ---- max over ranks

@@ -64,8 +64,11 @@ template <int HDP, bool KV> struct UbSmem {
                             BARS = STAT + (KV ? SB * 512 : 0), TOTAL = BARS + 128;
 };
 
-template <int HDP, bool TMA, bool KV>
-__global__ void __launch_bounds__(UB_THREADS, 2)
+// MW = number of math warpgroups (1 or 2).  The score math has no cross-column dependency (row statistics come
+// from the forward / the delta kernel), so with MW = 2 each thread owns HALF of its row's 64 streamed columns:
+// twice the warps in flight per scheduler for a latency-bound exp2/FMA loop, half the per-step critical path.
+template <int HDP, bool TMA, bool KV, int MW>
+__global__ void __launch_bounds__(128 + 128 * MW, 2)
 fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_constant__ CUtensorMap map_qkv64,
                    const __grid_constant__ CUtensorMap map_do, const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                    const float* __restrict__ lse2, const float* __restrict__ delta, bf16* __restrict__ dqkv,
@@ -109,7 +112,7 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
     if (base & 1023u) __trap();
     ua_mbar_init(r_ready, 32);
     for (int i = 0; i < NST; ++i) { ua_mbar_init(c_full + 8 * i, TMA ? 1 : UB_LOADERS); ua_mbar_init(c_empty + 8 * i, 1); }
-    ua_mbar_init(t_full, 1); ua_mbar_init(t_free, 128); ua_mbar_init(p_full, 128); ua_mbar_init(o_done, 1);
+    ua_mbar_init(t_full, 1); ua_mbar_init(t_free, 128 * MW); ua_mbar_init(p_full, 128 * MW); ua_mbar_init(o_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -122,7 +125,7 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
   const uint32_t tmem = *tmem_slot_ptr;
 
   if (warp < 4) {
-  ua_reg_dec<56>();
+  ua_reg_dec<MW == 2 ? 40 : 56>();
   if (warp == 0 || (!TMA && (warp == 2 || warp == 3))) {
     // ============================ loader ============================
     const int ld_tid = warp == 0 ? lane : (warp - 1) * 32 + lane;     // 0..95 on the cp.async path
@@ -230,9 +233,13 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
     }
   }
   } else {
-    ua_reg_inc<200>();
+    // register pool per CTA: 256 x 128 (MW = 1) -> 128 x 56 + 128 x 200; 384 x 80 (MW = 2) -> 128 x 40 + 256 x 96
+    ua_reg_inc<MW == 2 ? 96 : 200>();
     // ============================ score math ============================
     const int q = warp & 3;
+    const int wg = (warp - 4) >> 2;                           // math warpgroup: columns [wg * CW, +CW) of every step
+    constexpr int CW = UB_BN / MW;
+    const int col0 = wg * CW;
     const int row = q * 32 + lane;                            // TMEM lane = stationary row in tile
     const uint32_t t_1 = tmem + ((uint32_t)(q * 32) << 16);
     const int ri = r0 + row;
@@ -240,31 +247,31 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
     if (!KV && ri < N) { my_l2 = lse_bh[ri]; my_dl = delta_bh[ri]; }
     float* stat = reinterpret_cast<float*>(ub_raw + L::STAT);
     float my_stat = 0.f;
-    if (KV) my_stat = __ldg((row < 64 ? lse_bh : delta_bh - 64) + row);   // tile 0 (rows are padded to n_pad with zeros)
+    if (KV && wg == 0) my_stat = __ldg((row < 64 ? lse_bh : delta_bh - 64) + row);   // tile 0 (rows are padded to n_pad with zeros)
     for (int t = 0; t < T; ++t) {
       ua_mbar_wait(t_full, t & 1);
       ua_fence_after();
-      float s[64], dp[64];
-      ua_ld32(t_1, s); ua_ld32(t_1 + 32, s + 32);
-      ua_ld32(t_1 + UB_T2_COL, dp); ua_ld32(t_1 + UB_T2_COL + 32, dp + 32);
+      float s[CW], dp[CW];
+#pragma unroll
+      for (int c = 0; c < CW; c += 32) { ua_ld32(t_1 + col0 + c, s + c); ua_ld32(t_1 + UB_T2_COL + col0 + c, dp + c); }
       ua_ld_wait();
       ua_fence_before();
       ua_mbar_arrive(t_free);
-      uint32_t pk_p[KV ? 32 : 1], pk_d[32];
+      uint32_t pk_p[KV ? CW / 2 : 1], pk_d[CW / 2];
       // per-column statistics of this query tile: thread i publishes ONE value (i < 64: lse2 of column i,
       // else delta of column i - 64) that it loaded a whole step earlier, so no thread ever waits on global
       // memory; everybody then reads the 2 x 256 bytes as shared-memory broadcasts
       if constexpr (KV) {
         float* sb = stat + (t % L::SB) * 128;
-        if (L::SB == 1) asm volatile("bar.sync 1, 128;" ::: "memory");     // previous tile's readers are done
-        sb[row] = my_stat;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (t + 1 < T) my_stat = __ldg((row < 64 ? lse_bh : delta_bh - 64) + (t + 1) * UB_BN + row);
+        if (L::SB == 1) asm volatile("bar.sync 1, %0;" ::"n"(128 * MW) : "memory");   // previous tile's readers are done
+        if (wg == 0) sb[row] = my_stat;
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * MW) : "memory");
+        if (wg == 0 && t + 1 < T) my_stat = __ldg((row < 64 ? lse_bh : delta_bh - 64) + (t + 1) * UB_BN + row);
       }
-      const float* st_l2 = stat + (KV ? (t % L::SB) * 128 : 0);
+      const float* st_l2 = stat + (KV ? (t % L::SB) * 128 : 0) + col0;
       const float* st_dl = st_l2 + 64;
 #pragma unroll
-      for (int j = 0; j < 64; j += 4) {
+      for (int j = 0; j < CW; j += 4) {
         float l2[4], dl[4];
         if constexpr (KV) {
           const float4 a = *reinterpret_cast<const float4*>(st_l2 + j);
@@ -287,8 +294,8 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
       if (t > 0) ua_mbar_wait(o_done, (t - 1) & 1);           // output MMAs of step t-1 done: P / dS smem is ours
       ua_fence_after();
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {                           // 8 chunks of 8 streamed columns
-        const uint32_t off = row * 128 + ((c ^ (row & 7)) << 4);
+      for (int c = 0; c < CW / 8; ++c) {                      // my chunks of 8 streamed columns
+        const uint32_t off = row * 128 + (((col0 / 8 + c) ^ (row & 7)) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + off), "r"(pk_d[4 * c]), "r"(pk_d[4 * c + 1]),
                      "r"(pk_d[4 * c + 2]), "r"(pk_d[4 * c + 3]) : "memory");
         if constexpr (KV)
@@ -309,6 +316,7 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
       const uint32_t t_o = t_1 + (o == 0 ? UB_O1_COL : UB_O2_COL);
 #pragma unroll
       for (int c = 0; c < HDP; c += 32) {
+        if ((o * (HDP / 32) + c / 32) % MW != wg) continue;   // 32-column output blocks round-robin over the warpgroups
         float v[32];
         ua_ld32(t_o + c, v);
         ua_ld_wait();
@@ -346,26 +354,26 @@ bool avj_attention_umma_bwd_supported(int dtype, int hd) {
   return dtype == AVJ_BF16 && hd % 8 == 0 && hd >= 8 && hd <= 64;
 }
 
-template <int HDP, bool TMA, bool KV>
+template <int HDP, bool TMA, bool KV, int MW>
 static int ub_launch(const CUtensorMap& m128, const CUtensorMap& m64, const CUtensorMap& mdo, const bf16* qkv, const bf16* dout,
                      const float* lse2, const float* delta, bf16* dqkv, int B, int N, int n_pad, int H, int hd, float scale,
                      cudaStream_t s) {
   static bool set = false;
   const int smem = (int)UbSmem<HDP, KV>::TOTAL;
   if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(fa_bwd_umma_kernel<HDP, TMA, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(fa_bwd_umma_kernel<HDP, TMA, KV, MW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     AVJ_CHECK(e == cudaSuccess, "cudaFuncSetAttribute(fa_bwd_umma_kernel) failed: %s", cudaGetErrorString(e));
-    cudaFuncSetAttribute(fa_bwd_umma_kernel<HDP, TMA, KV>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(fa_bwd_umma_kernel<HDP, TMA, KV, MW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     set = true;
   }
   dim3 grid((N + UB_BM - 1) / UB_BM, H, B);
-  fa_bwd_umma_kernel<HDP, TMA, KV><<<grid, UB_THREADS, smem, s>>>(m128, m64, mdo, qkv, dout, lse2, delta, dqkv, N, n_pad, H, hd, scale,
+  fa_bwd_umma_kernel<HDP, TMA, KV, MW><<<grid, 128 + 128 * MW, smem, s>>>(m128, m64, mdo, qkv, dout, lse2, delta, dqkv, N, n_pad, H, hd, scale,
                                                                   scale * 1.4426950408889634f);
   AVJ_LAUNCH_CHECK();
   return 0;
 }
 
-template <int HDP, bool TMA>
+template <int HDP, bool TMA, int MW>
 static int ub_both(const bf16* qkv, const bf16* dout, const float* lse2, const float* delta, bf16* dqkv,
                    int B, int N, int n_pad, int H, int hd, float scale, cudaStream_t s) {
   CUtensorMap m128, m64, mdo64, mdo128;
@@ -377,9 +385,9 @@ static int ub_both(const bf16* qkv, const bf16* dout, const float* lse2, const f
     if ((rc = ua_make_map3d(dout, B, N, H * hd, 64, &mdo64, HDP))) return rc;
     if ((rc = ua_make_map3d(dout, B, N, H * hd, 128, &mdo128, HDP))) return rc;
   }
-  int rc = ub_launch<HDP, TMA, true>(m128, m64, mdo64, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
+  int rc = ub_launch<HDP, TMA, true, MW>(m128, m64, mdo64, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
   if (rc) return rc;
-  return ub_launch<HDP, TMA, false>(m128, m64, mdo128, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
+  return ub_launch<HDP, TMA, false, MW>(m128, m64, mdo128, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
 }
 
 int avj_attention_bwd_umma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* ws,
@@ -395,12 +403,16 @@ int avj_attention_bwd_umma(const void* qkv, const void* out, const void* dout, c
   static int use_tma32 = -1;   // AVJ_ATTN_TMA32=0: head_dim <= 32 goes back to the cp.async gather loaders
   if (use_tma32 < 0) { const char* e = getenv("AVJ_ATTN_TMA32"); use_tma32 = (e && e[0] == '0') ? 0 : use_tma; }
   const bool aligned = ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(dout)) & 15) == 0;
+  static int mw = -1;          // AVJ_ATTN_BWD_MW=1: one math warpgroup (256-thread CTAs) instead of two
+  if (mw < 0) { const char* e = getenv("AVJ_ATTN_BWD_MW"); mw = (e && e[0] == '1') ? 1 : 2; }
+#define UB_GO(HDP_, TMA_)                                                                                                    \
+  return mw == 2 ? ub_both<HDP_, TMA_, 2>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, B, N, n_pad, H, hd, scale, s) \
+                 : ub_both<HDP_, TMA_, 1>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, B, N, n_pad, H, hd, scale, s)
   if (hd <= 32) {
-    if (use_tma32 && aligned)
-      return ub_both<32, true>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, B, N, n_pad, H, hd, scale, s);
-    return ub_both<32, false>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, B, N, n_pad, H, hd, scale, s);
+    if (use_tma32 && aligned) { UB_GO(32, true); }
+    UB_GO(32, false);
   }
-  if (hd == 64 && use_tma && aligned)
-    return ub_both<64, true>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, B, N, n_pad, H, hd, scale, s);
-  return ub_both<64, false>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, B, N, n_pad, H, hd, scale, s);
+  if (hd == 64 && use_tma && aligned) { UB_GO(64, true); }
+  UB_GO(64, false);
+#undef UB_GO
 }

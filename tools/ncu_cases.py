@@ -21,6 +21,8 @@ CASES = {
     'gemm_dact': lambda: kb.bench_gemm(GEMM_NN, R_C, 4096, 1024, 'dact', 'ctx fc2 dgrad'),
     'gemm_wgrad': lambda: kb.bench_gemm(GEMM_TN, 4096, 1024, R_C, 'accum', 'ctx fc1 wgrad'),
     'gemm_pred_fc1': lambda: kb.bench_gemm(GEMM_NT, R_P, 1536, 384, 'gelu', 'pred fc1'),
+    'gemm_pred_qkv': lambda: kb.bench_gemm(GEMM_NT, R_P, 1152, 384, 'bias', 'pred qkv'),
+    'gemm_pred_dact': lambda: kb.bench_gemm(GEMM_NN, R_P, 1536, 384, 'dact', 'pred fc2 dgrad'),
     'gemm_square': lambda: kb.bench_gemm(GEMM_NT, 8192, 8192, 8192, 'none', 'square 8192'),
     'attn_target': lambda: kb.bench_attn(24, 1664, 16, 64, 'target enc'),
     'attn_pred': lambda: kb.bench_attn(24, 1216, 16, 24, 'predictor'),

@@ -233,6 +233,8 @@ __global__ void __launch_bounds__(256)
 fa_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, float* __restrict__ delta,
                 const float* __restrict__ lse, float* __restrict__ lse2_out, float scale, int n_pad,
                 int B, int N, int H, int hd) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t total = (int64_t)B * n_pad * H;
   for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < total; w += (int64_t)gridDim.x * blockDim.x) {
     const int h = (int)(w % H);
@@ -489,7 +491,7 @@ int avj_attention_delta(const void* out, const void* dout, float* delta, const f
   int grid = (int)((threads + 255) / 256);
   const int cap = avj_num_sms() * 16;
   if (grid > cap) grid = cap;
-  fa_delta_kernel<<<grid, 256, 0, s>>>((const bf16*)out, (const bf16*)dout, delta, lse, lse2_out, scale, n_pad, B, N, H, hd);
+  avj_launch_pdl(fa_delta_kernel, dim3(grid), dim3(256), 0, s, (const bf16*)out, (const bf16*)dout, delta, lse, lse2_out, scale, n_pad, B, N, H, hd);
   AVJ_LAUNCH_CHECK();
   return 0;
 }

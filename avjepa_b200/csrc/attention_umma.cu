@@ -44,11 +44,13 @@ template <int HDP> struct UaSmem {
 };
 #define UA_TMEM_COLS 256
 #define UA_O_COL 128
+#define UA_P_COL 192               // TS: 64 columns of packed bf16 P (128 keys)
 
 // TMA = true (hd == 64): one elected thread issues 16 KB box loads (rows past N are zero-filled by
 // the hardware); TMA = false: the loader warp gathers 16-byte chunks with cp.async and pads in smem.
 // POLY: every fourth pair of scores takes ua_exp2_poly (FMA pipe) instead of MUFU ex2.
-template <int HDP, bool TMA, bool POLY>
+// TS: P goes to tensor memory (packed bf16, columns [192, 256)) and is the A operand of the PV MMA from there.
+template <int HDP, bool TMA, bool POLY, bool TS>
 __global__ void __launch_bounds__(UA_THREADS, 2)
 fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restrict__ qkv, bf16* __restrict__ out,
                    float* __restrict__ lse, int N, int H, int hd, float scale_log2) {
@@ -73,6 +75,7 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
   const uint32_t q_ready = bars + 104;      // count 32: Q pad columns zeroed (TMA path, hd < HDP)
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(ua_raw + (tmem_slot - base));
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * UA_BM;
   // A TMA box always spans HDP columns: for hd < HDP columns [hd, HDP) of every tile hold the NEXT head's
@@ -100,6 +103,7 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
   __syncthreads();
   ua_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
+  pdl_wait();
 
   if (warp < 4) {
   ua_reg_dec<48>();
@@ -177,7 +181,8 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
         for (int k = 0; k < UA_BN / 16; ++k) {
           const uint64_t pd = ua_desc(sP + (k >> 2) * UA_P_TILE, 1, 64) + 2 * (k & 3);
           const uint64_t vd = TL::mnmajor(vt) + TL::MN_KADV * k;     // MN-major: 16 keys per step
-          ua_mma(tmem + UA_O_COL, pd, vd, idesc_o, (t > 0 || k > 0) ? 1u : 0u);
+          if (TS) ua_mma_ts(tmem + UA_O_COL, tmem + UA_P_COL + 8 * k, vd, idesc_o, (t > 0 || k > 0) ? 1u : 0u);
+          else    ua_mma(tmem + UA_O_COL, pd, vd, idesc_o, (t > 0 || k > 0) ? 1u : 0u);
         }
         ua_commit(o_done);
         ua_commit(kv_empty + 8 * (t % NST));
@@ -233,11 +238,16 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
       m = m_use;
       if (t > 0) ua_mbar_wait(o_done, (t - 1) & 1);                  // PV[t-1] finished: P smem and O are ours
       ua_fence_after();
+      if constexpr (TS) {
+        ua_st_regs<32>(t_s + UA_P_COL, pk);
+        ua_st_regs<32>(t_s + UA_P_COL + 32, pk + 32);
+      } else {
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {                                 // 16 chunks of 8 keys
-        const uint32_t dst = sP + (c >> 3) * UA_P_TILE + row * 128 + (((c & 7) ^ (row & 7)) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
-                     "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
+        for (int c = 0; c < 16; ++c) {                               // 16 chunks of 8 keys
+          const uint32_t dst = sP + (c >> 3) * UA_P_TILE + row * 128 + (((c & 7) ^ (row & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
+                       "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
+        }
       }
       if (t > 0 && __any_sync(0xffffffffu, jump)) {
         float o[32];
@@ -250,7 +260,7 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
           ua_st32(t_o + c, o);
         }
       }
-      ua_fence_async_smem();
+      if constexpr (TS) ua_st_wait(); else ua_fence_async_smem();
       ua_fence_before();
       ua_mbar_arrive(p_full);
     };
@@ -338,14 +348,14 @@ int ua_make_map3d(const void* qkv, int B, int N, int cols, int box_rows, CUtenso
   return 0;
 }
 
-template <int HDP, bool TMA, bool POLY>
+template <int HDP, bool TMA, bool POLY, bool TS>
 static int ua_launch(const bf16* qkv, bf16* out, float* lse, int B, int N, int H, int hd, float scale, cudaStream_t s) {
   static bool set = false;
   if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(fa_fwd_umma_kernel<HDP, TMA, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UaSmem<HDP>::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(fa_fwd_umma_kernel<HDP, TMA, POLY, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UaSmem<HDP>::TOTAL);
     AVJ_CHECK(e == cudaSuccess, "cudaFuncSetAttribute(fa_fwd_umma_kernel) failed: %s", cudaGetErrorString(e));
     // two CTAs per SM need the full 228 KB shared-memory carve-out
-    cudaFuncSetAttribute(fa_fwd_umma_kernel<HDP, TMA, POLY>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(fa_fwd_umma_kernel<HDP, TMA, POLY, TS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     set = true;
   }
   CUtensorMap map;
@@ -355,7 +365,7 @@ static int ua_launch(const bf16* qkv, bf16* out, float* lse, int B, int N, int H
     if (rc) return rc;
   }
   dim3 grid((N + UA_BM - 1) / UA_BM, H, B);
-  fa_fwd_umma_kernel<HDP, TMA, POLY><<<grid, UA_THREADS, UaSmem<HDP>::TOTAL, s>>>(map, qkv, out, lse, N, H, hd, scale * 1.4426950408889634f);
+  avj_launch_pdl(fa_fwd_umma_kernel<HDP, TMA, POLY, TS>, grid, dim3(UA_THREADS), UaSmem<HDP>::TOTAL, s, map, qkv, out, lse, N, H, hd, scale * 1.4426950408889634f);
   AVJ_LAUNCH_CHECK();
   return 0;
 }
@@ -368,9 +378,14 @@ int avj_attention_fwd_umma(const void* qkv, void* out, float* lse, int B, int N,
   static int use_poly = -1;    // AVJ_ATTN_POLY=1: a quarter of the exp2 evaluations on the FMA pipe
   if (use_poly < 0) { const char* e = getenv("AVJ_ATTN_POLY"); use_poly = (e && e[0] == '1') ? 1 : 0; }
   const bool al = (reinterpret_cast<uintptr_t>(qkv) & 15) == 0;
-#define UA_GO(HDP_, TMA_) \
-  return use_poly ? ua_launch<HDP_, TMA_, true>((const bf16*)qkv, (bf16*)out, lse, B, N, H, hd, scale, s) \
-                  : ua_launch<HDP_, TMA_, false>((const bf16*)qkv, (bf16*)out, lse, B, N, H, hd, scale, s)
+  static int ts = -1;          // AVJ_ATTN_TMEM_P=0: P through shared memory instead of tensor memory
+  if (ts < 0) { const char* e = getenv("AVJ_ATTN_TMEM_P"); ts = (e && e[0] == '0') ? 0 : 1; }
+#define UA_ARGS (const bf16*)qkv, (bf16*)out, lse, B, N, H, hd, scale, s
+#define UA_GO(HDP_, TMA_)                                                                             \
+  {                                                                                                   \
+    if (ts) return use_poly ? ua_launch<HDP_, TMA_, true, true>(UA_ARGS) : ua_launch<HDP_, TMA_, false, true>(UA_ARGS);   \
+    return use_poly ? ua_launch<HDP_, TMA_, true, false>(UA_ARGS) : ua_launch<HDP_, TMA_, false, false>(UA_ARGS);         \
+  }
   if (hd <= 32) {
     if (use_tma32 && al) { UA_GO(32, true); }
     UA_GO(32, false);
@@ -378,4 +393,5 @@ int avj_attention_fwd_umma(const void* qkv, void* out, float* lse, int B, int N,
   if (hd == 64 && use_tma && al) { UA_GO(64, true); }
   UA_GO(64, false);
 #undef UA_GO
+#undef UA_ARGS
 }

@@ -67,7 +67,9 @@ template <int HDP, bool KV> struct UbSmem {
 // MW = number of math warpgroups (1 or 2).  The score math has no cross-column dependency (row statistics come
 // from the forward / the delta kernel), so with MW = 2 each thread owns HALF of its row's 64 streamed columns:
 // twice the warps in flight per scheduler for a latency-bound exp2/FMA loop, half the per-step critical path.
-template <int HDP, bool TMA, bool KV, int MW>
+// TS (HDP == 32 only: 2 x 64 score + 2 x 32 output + 2 x 32 operand columns = 256): P^T / dS^T are written to
+// tensor memory as packed bf16 and consumed as the A operand of the output MMAs from there.
+template <int HDP, bool TMA, bool KV, int MW, bool TS>
 __global__ void __launch_bounds__(128 + 128 * MW, 2)
 fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_constant__ CUtensorMap map_qkv64,
                    const __grid_constant__ CUtensorMap map_do, const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
@@ -76,6 +78,9 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
   using L = UbSmem<HDP, KV>;
   using TL = UaTile<HDP>;
   constexpr int NST = L::NST;
+  static_assert(!TS || HDP == 32, "operands in TMEM need the 256-column budget of HDP = 32");
+  constexpr uint32_t O1_COL = UB_O1_COL, O2_COL = TS ? UB_O1_COL + 32 : UB_O2_COL;
+  constexpr uint32_t PT_COL = 192, DST_COL = 224;             // TS: packed bf16 P^T / dS^T, 32 columns each
   extern __shared__ __align__(1024) uint8_t ub_raw[];
   const uint32_t base = ua_smem(ub_raw);
   const uint32_t sR1 = base + L::R1, sR2 = base + L::R2, sC1 = base + L::C1, sC2 = base + L::C2;
@@ -91,6 +96,7 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
   const uint32_t r_ready = bars + 104;      // count 32: pad columns of the stationary tiles zeroed (TMA, hd < HDP)
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(ub_raw + L::BARS + 96);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, r0 = blockIdx.x * UB_BM;
   const int64_t rs = 3 * (int64_t)H * hd;                    // qkv row stride (elements)
@@ -123,6 +129,7 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
   __syncthreads();
   ua_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
+  pdl_wait();
 
   if (warp < 4) {
   ua_reg_dec<MW == 2 ? 40 : 56>();
@@ -220,12 +227,21 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
           const uint64_t pd = ua_desc(sP, 1, 64);
           const uint64_t c2m = TL::mnmajor(c2);
 #pragma unroll
-          for (int k = 0; k < UB_BN / 16; ++k) ua_mma(tmem + UB_O1_COL, pd + 2 * k, c2m + TL::MN_KADV * k, idesc_o, (accum0 | (k > 0)) ? 1u : 0u);   // dV += P^T dO
+          for (int k = 0; k < UB_BN / 16; ++k) {                                               // dV += P^T dO
+            if (TS) ua_mma_ts(tmem + O1_COL, tmem + PT_COL + 8 * k, c2m + TL::MN_KADV * k, idesc_o, (accum0 | (k > 0)) ? 1u : 0u);
+            else    ua_mma(tmem + O1_COL, pd + 2 * k, c2m + TL::MN_KADV * k, idesc_o, (accum0 | (k > 0)) ? 1u : 0u);
+          }
 #pragma unroll
-          for (int k = 0; k < UB_BN / 16; ++k) ua_mma(tmem + UB_O2_COL, dsd + 2 * k, c1m + TL::MN_KADV * k, idesc_o, (accum0 | (k > 0)) ? 1u : 0u);  // dK += dS^T Q
+          for (int k = 0; k < UB_BN / 16; ++k) {                                               // dK += dS^T Q
+            if (TS) ua_mma_ts(tmem + O2_COL, tmem + DST_COL + 8 * k, c1m + TL::MN_KADV * k, idesc_o, (accum0 | (k > 0)) ? 1u : 0u);
+            else    ua_mma(tmem + O2_COL, dsd + 2 * k, c1m + TL::MN_KADV * k, idesc_o, (accum0 | (k > 0)) ? 1u : 0u);
+          }
         } else {
 #pragma unroll
-          for (int k = 0; k < UB_BN / 16; ++k) ua_mma(tmem + UB_O1_COL, dsd + 2 * k, c1m + TL::MN_KADV * k, idesc_o, (accum0 | (k > 0)) ? 1u : 0u);  // dQ += dS K
+          for (int k = 0; k < UB_BN / 16; ++k) {                                               // dQ += dS K
+            if (TS) ua_mma_ts(tmem + O1_COL, tmem + DST_COL + 8 * k, c1m + TL::MN_KADV * k, idesc_o, (accum0 | (k > 0)) ? 1u : 0u);
+            else    ua_mma(tmem + O1_COL, dsd + 2 * k, c1m + TL::MN_KADV * k, idesc_o, (accum0 | (k > 0)) ? 1u : 0u);
+          }
         }
         ua_commit(o_done);
         ua_commit(c_empty + 8 * (t % NST));
@@ -293,16 +309,22 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
       }
       if (t > 0) ua_mbar_wait(o_done, (t - 1) & 1);           // output MMAs of step t-1 done: P / dS smem is ours
       ua_fence_after();
+      if constexpr (TS) {
+        ua_st_regs<CW / 2>(t_1 + DST_COL + col0 / 2, pk_d);
+        if constexpr (KV) ua_st_regs<CW / 2>(t_1 + PT_COL + col0 / 2, pk_p);
+        ua_st_wait();
+      } else {
 #pragma unroll
-      for (int c = 0; c < CW / 8; ++c) {                      // my chunks of 8 streamed columns
-        const uint32_t off = row * 128 + (((col0 / 8 + c) ^ (row & 7)) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + off), "r"(pk_d[4 * c]), "r"(pk_d[4 * c + 1]),
-                     "r"(pk_d[4 * c + 2]), "r"(pk_d[4 * c + 3]) : "memory");
-        if constexpr (KV)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + off), "r"(pk_p[4 * c]), "r"(pk_p[4 * c + 1]),
-                       "r"(pk_p[4 * c + 2]), "r"(pk_p[4 * c + 3]) : "memory");
+        for (int c = 0; c < CW / 8; ++c) {                    // my chunks of 8 streamed columns
+          const uint32_t off = row * 128 + (((col0 / 8 + c) ^ (row & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + off), "r"(pk_d[4 * c]), "r"(pk_d[4 * c + 1]),
+                       "r"(pk_d[4 * c + 2]), "r"(pk_d[4 * c + 3]) : "memory");
+          if constexpr (KV)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + off), "r"(pk_p[4 * c]), "r"(pk_p[4 * c + 1]),
+                         "r"(pk_p[4 * c + 2]), "r"(pk_p[4 * c + 3]) : "memory");
+        }
+        ua_fence_async_smem();
       }
-      ua_fence_async_smem();
       ua_fence_before();
       ua_mbar_arrive(p_full);
     }
@@ -313,7 +335,7 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
 #pragma unroll
     for (int o = 0; o < (KV ? 2 : 1); ++o) {
       const int slot = KV ? (o == 0 ? 2 : 1) : 0;
-      const uint32_t t_o = t_1 + (o == 0 ? UB_O1_COL : UB_O2_COL);
+      const uint32_t t_o = t_1 + (o == 0 ? O1_COL : O2_COL);
 #pragma unroll
       for (int c = 0; c < HDP; c += 32) {
         if ((o * (HDP / 32) + c / 32) % MW != wg) continue;   // 32-column output blocks round-robin over the warpgroups
@@ -354,26 +376,26 @@ bool avj_attention_umma_bwd_supported(int dtype, int hd) {
   return dtype == AVJ_BF16 && hd % 8 == 0 && hd >= 8 && hd <= 64;
 }
 
-template <int HDP, bool TMA, bool KV, int MW>
+template <int HDP, bool TMA, bool KV, int MW, bool TS>
 static int ub_launch(const CUtensorMap& m128, const CUtensorMap& m64, const CUtensorMap& mdo, const bf16* qkv, const bf16* dout,
                      const float* lse2, const float* delta, bf16* dqkv, int B, int N, int n_pad, int H, int hd, float scale,
                      cudaStream_t s) {
   static bool set = false;
   const int smem = (int)UbSmem<HDP, KV>::TOTAL;
   if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(fa_bwd_umma_kernel<HDP, TMA, KV, MW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(fa_bwd_umma_kernel<HDP, TMA, KV, MW, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     AVJ_CHECK(e == cudaSuccess, "cudaFuncSetAttribute(fa_bwd_umma_kernel) failed: %s", cudaGetErrorString(e));
-    cudaFuncSetAttribute(fa_bwd_umma_kernel<HDP, TMA, KV, MW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(fa_bwd_umma_kernel<HDP, TMA, KV, MW, TS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     set = true;
   }
   dim3 grid((N + UB_BM - 1) / UB_BM, H, B);
-  fa_bwd_umma_kernel<HDP, TMA, KV, MW><<<grid, 128 + 128 * MW, smem, s>>>(m128, m64, mdo, qkv, dout, lse2, delta, dqkv, N, n_pad, H, hd, scale,
-                                                                  scale * 1.4426950408889634f);
+  avj_launch_pdl(fa_bwd_umma_kernel<HDP, TMA, KV, MW, TS>, grid, dim3(128 + 128 * MW), (size_t)smem, s, m128, m64, mdo, qkv, dout, lse2, delta, dqkv, N, n_pad,
+                 H, hd, scale, scale * 1.4426950408889634f);
   AVJ_LAUNCH_CHECK();
   return 0;
 }
 
-template <int HDP, bool TMA, int MW>
+template <int HDP, bool TMA, int MW, bool TS>
 static int ub_both(const bf16* qkv, const bf16* dout, const float* lse2, const float* delta, bf16* dqkv,
                    int B, int N, int n_pad, int H, int hd, float scale, cudaStream_t s) {
   CUtensorMap m128, m64, mdo64, mdo128;
@@ -385,9 +407,9 @@ static int ub_both(const bf16* qkv, const bf16* dout, const float* lse2, const f
     if ((rc = ua_make_map3d(dout, B, N, H * hd, 64, &mdo64, HDP))) return rc;
     if ((rc = ua_make_map3d(dout, B, N, H * hd, 128, &mdo128, HDP))) return rc;
   }
-  int rc = ub_launch<HDP, TMA, true, MW>(m128, m64, mdo64, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
+  int rc = ub_launch<HDP, TMA, true, MW, TS>(m128, m64, mdo64, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
   if (rc) return rc;
-  return ub_launch<HDP, TMA, false, MW>(m128, m64, mdo128, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
+  return ub_launch<HDP, TMA, false, MW, TS>(m128, m64, mdo128, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
 }
 
 int avj_attention_bwd_umma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* ws,
@@ -405,14 +427,17 @@ int avj_attention_bwd_umma(const void* qkv, const void* out, const void* dout, c
   const bool aligned = ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(dout)) & 15) == 0;
   static int mw = -1;          // AVJ_ATTN_BWD_MW=1: one math warpgroup (256-thread CTAs) instead of two
   if (mw < 0) { const char* e = getenv("AVJ_ATTN_BWD_MW"); mw = (e && e[0] == '1') ? 1 : 2; }
-#define UB_GO(HDP_, TMA_)                                                                                                    \
-  return mw == 2 ? ub_both<HDP_, TMA_, 2>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, B, N, n_pad, H, hd, scale, s) \
-                 : ub_both<HDP_, TMA_, 1>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, B, N, n_pad, H, hd, scale, s)
+  static int ts = -1;          // AVJ_ATTN_TMEM_P=0: P^T / dS^T through shared memory for head_dim <= 32 as well
+  if (ts < 0) { const char* e = getenv("AVJ_ATTN_TMEM_P"); ts = (e && e[0] == '0') ? 0 : 1; }
+#define UB_ARGS (const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, B, N, n_pad, H, hd, scale, s
+#define UB_GO(HDP_, TMA_, TS_) return mw == 2 ? ub_both<HDP_, TMA_, 2, TS_>(UB_ARGS) : ub_both<HDP_, TMA_, 1, TS_>(UB_ARGS)
   if (hd <= 32) {
-    if (use_tma32 && aligned) { UB_GO(32, true); }
-    UB_GO(32, false);
+    if (use_tma32 && aligned) { if (ts) { UB_GO(32, true, true); } UB_GO(32, true, false); }
+    if (ts) { UB_GO(32, false, true); }
+    UB_GO(32, false, false);
   }
-  if (hd == 64 && use_tma && aligned) { UB_GO(64, true); }
-  UB_GO(64, false);
+  if (hd == 64 && use_tma && aligned) { UB_GO(64, true, false); }
+  UB_GO(64, false, false);
+#undef UB_ARGS
 #undef UB_GO
 }

@@ -7,6 +7,12 @@
 #include <mutex>
 #include <vector>
 
+bool avj_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("AVJ_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 // ---- kernel timing ---------------------------------------------------------------------------
 bool g_avj_prof_on = false;
 namespace {

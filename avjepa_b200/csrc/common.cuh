@@ -45,6 +45,35 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 
 int avj_num_sms();
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// A step is ~2400 dependent launches of 10-400 us kernels, so the per-boundary cost (grid drain, launch
+// processing, the next kernel's barrier-init / TMEM-alloc / descriptor-fetch prologue) is a visible share of
+// the step.  Kernels launched through avj_launch_pdl carry cudaLaunchAttributeProgrammaticStreamSerialization:
+// they may be scheduled while their predecessor in the stream is still running.  Every such kernel
+//   * calls pdl_trigger() first (lets ITS successor be scheduled as early as possible), then
+//   * does only predecessor-independent set-up (shared memory, barriers, TMEM, kernel-parameter reads), and
+//   * calls pdl_wait() -- which returns once the predecessor grid has completed and flushed -- before its
+//     first global-memory access.
+// Only kernels that contain pdl_wait() may be launched this way.  AVJ_PDL=0 drops the attribute (the device
+// instructions are no-ops for a normally launched grid).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool avj_pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t avj_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                         Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = avj_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- in-library kernel timing (avj_prof_*): when enabled every instrumented entry point brackets its
 // launches with CUDA events on the launch stream; bench.py reads per-family totals for the roofline.
 enum { AVJ_FAM_GEMM = 0, AVJ_FAM_ATTN_FWD = 1, AVJ_FAM_ATTN_BWD = 2, AVJ_FAM_LN_FWD = 3, AVJ_FAM_LN_BWD = 4,

@@ -234,6 +234,8 @@ __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const T* __restrict__ in, int ld, avj_rowmap map, float* __restrict__ ws,
                       int rows, int D, int chunk) {
   __shared__ float sm[8][32][8 + 1];
+  pdl_trigger();
+  pdl_wait();
   const int c0 = (blockIdx.x * 32 + threadIdx.x) * 8;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (c0 < D) {
@@ -270,6 +272,8 @@ colsum_partial_kernel(const T* __restrict__ in, int ld, avj_rowmap map, float* _
 }
 
 __global__ void colsum_final_kernel(const float* __restrict__ ws, float* __restrict__ out, int ny, int D) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= D) return;
   float s = 0.f;
@@ -293,11 +297,11 @@ extern "C" int avj_colsum(const void* in, int in_dtype, int ld, avj_rowmap map, 
   ny = (rows + chunk - 1) / chunk;
   dim3 grid(gx, ny), block(32, 8);
   if (in_dtype == AVJ_BF16)
-    colsum_partial_kernel<bf16><<<grid, block, 0, as_stream(stream)>>>((const bf16*)in, ld, map, ws, rows, D, chunk);
+    avj_launch_pdl(colsum_partial_kernel<bf16>, grid, block, 0, as_stream(stream), (const bf16*)in, ld, map, ws, rows, D, chunk);
   else
-    colsum_partial_kernel<float><<<grid, block, 0, as_stream(stream)>>>((const float*)in, ld, map, ws, rows, D, chunk);
+    avj_launch_pdl(colsum_partial_kernel<float>, grid, block, 0, as_stream(stream), (const float*)in, ld, map, ws, rows, D, chunk);
   AVJ_LAUNCH_CHECK();
-  colsum_final_kernel<<<(D + 63) / 64, 64, 0, as_stream(stream)>>>(ws, out, ny, D);
+  avj_launch_pdl(colsum_final_kernel, dim3((D + 63) / 64), dim3(64), 0, as_stream(stream), ws, out, ny, D);
   AVJ_LAUNCH_CHECK();
   return 0;
 }
@@ -308,6 +312,8 @@ __global__ void __launch_bounds__(256)
 colsum2_partial_kernel(const T* __restrict__ in1, int ld1, int D1, const T* __restrict__ in2, int ld2, int D2,
                        float* __restrict__ ws, int rows, int chunk, int gx1) {
   __shared__ float sm[8][32][8 + 1];
+  pdl_trigger();
+  pdl_wait();
   const bool second = (int)blockIdx.x >= gx1;
   const T* in = second ? in2 : in1;
   const int ld = second ? ld2 : ld1, D = second ? D2 : D1;
@@ -349,6 +355,8 @@ colsum2_partial_kernel(const T* __restrict__ in1, int ld1, int D1, const T* __re
 
 __global__ void colsum2_final_kernel(const float* __restrict__ ws, float* __restrict__ out1, float* __restrict__ out2,
                                      int ny, int D1, int D2) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= D1 + D2) return;
   float s = 0.f;
@@ -373,11 +381,11 @@ extern "C" int avj_colsum2(const void* in1, int ld1, int D1, float* out1, const 
   ny = (rows + chunk - 1) / chunk;
   dim3 grid(gx, ny), block(32, 8);
   if (in_dtype == AVJ_BF16)
-    colsum2_partial_kernel<bf16><<<grid, block, 0, as_stream(stream)>>>((const bf16*)in1, ld1, D1, (const bf16*)in2, ld2, D2, ws, rows, chunk, gx1);
+    avj_launch_pdl(colsum2_partial_kernel<bf16>, grid, block, 0, as_stream(stream), (const bf16*)in1, ld1, D1, (const bf16*)in2, ld2, D2, ws, rows, chunk, gx1);
   else
-    colsum2_partial_kernel<float><<<grid, block, 0, as_stream(stream)>>>((const float*)in1, ld1, D1, (const float*)in2, ld2, D2, ws, rows, chunk, gx1);
+    avj_launch_pdl(colsum2_partial_kernel<float>, grid, block, 0, as_stream(stream), (const float*)in1, ld1, D1, (const float*)in2, ld2, D2, ws, rows, chunk, gx1);
   AVJ_LAUNCH_CHECK();
-  colsum2_final_kernel<<<(D1 + D2 + 63) / 64, 64, 0, as_stream(stream)>>>(ws, out1, out2, ny, D1, D2);
+  avj_launch_pdl(colsum2_final_kernel, dim3((D1 + D2 + 63) / 64), dim3(64), 0, as_stream(stream), ws, out1, out2, ny, D1, D2);
   AVJ_LAUNCH_CHECK();
   return 0;
 }

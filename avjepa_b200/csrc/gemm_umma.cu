@@ -398,6 +398,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
@@ -414,6 +415,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();                 // barrier init, TMEM allocation and descriptor prefetch overlapped the previous kernel
 
   const int n_units = p.tiles_m * p.tiles_n * p.split_k;
 
@@ -596,6 +598,7 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
@@ -612,6 +615,7 @@ gemm_umma2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   cluster_sync_all();                                   // barrier inits + TMEM allocation visible pair-wide
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();
 
   const int n_units = p.tiles_m * p.tiles_n * p.split_k;   // tiles_m counts 256-row tiles here
   const int half_n = p.block_n / 2;
@@ -933,10 +937,10 @@ int avj_gemm_umma(int layout, const void* A, const void* B, void* C, int M, int 
   const int threads = 128 + 32 * (wide ? 16 : 8);
   if (two) {
     const int clusters = units < workers ? units : workers;
-    (p.tma_store ? kerns_ts[1][wide][epi] : kerns[1][wide][epi])<<<2 * clusters, threads, UG2_SMEM_BYTES, s>>>(ma, mb, mc, mp, p);
+    avj_launch_pdl(p.tma_store ? kerns_ts[1][wide][epi] : kerns[1][wide][epi], dim3(2 * clusters), dim3(threads), UG2_SMEM_BYTES, s, ma, mb, mc, mp, p);
   } else {
     const int grid = units < sms ? units : sms;
-    (p.tma_store ? kerns_ts[0][wide][epi] : kerns[0][wide][epi])<<<grid, threads, UG_SMEM_BYTES, s>>>(ma, mb, mc, mp, p);
+    avj_launch_pdl(p.tma_store ? kerns_ts[0][wide][epi] : kerns[0][wide][epi], dim3(grid), dim3(threads), UG_SMEM_BYTES, s, ma, mb, mc, mp, p);
   }
   AVJ_LAUNCH_CHECK();
   return 0;

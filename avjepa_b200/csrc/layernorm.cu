@@ -12,6 +12,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      TY* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                      int rows, int D, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = D / 4;
   for (int64_t r = (int64_t)blockIdx.x * LN_WARPS + warp; r < rows; r += (int64_t)gridDim.x * LN_WARPS) {
@@ -68,7 +70,7 @@ static int launch_ln_fwd(const float* x, const float* gamma, const float* beta, 
   int grid = (rows + LN_WARPS - 1) / LN_WARPS;
   const int cap = avj_num_sms() * 8;
   if (grid > cap) grid = cap;
-#define LN_CASE(NV) case NV: layernorm_fwd_kernel<TY, NV><<<grid, LN_WARPS * 32, 0, s>>>(x, gamma, beta, y, mean, rstd, rows, D, eps); break;
+#define LN_CASE(NV) case NV: avj_launch_pdl(layernorm_fwd_kernel<TY, NV>, dim3(grid), dim3(LN_WARPS * 32), 0, s, x, gamma, beta, y, mean, rstd, rows, D, eps); break;
   switch (nv4) {
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
     LN_CASE(9) LN_CASE(10) LN_CASE(11) LN_CASE(12) LN_CASE(13) LN_CASE(14) LN_CASE(15) LN_CASE(16)
@@ -124,6 +126,7 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ x, co
                      float* __restrict__ dx, TLP* __restrict__ dx_lp, float* __restrict__ ws, int want_dgamma,
                      int want_colsum, int rows, int D) {
   extern __shared__ float sm[];   // [LN_WARPS][3][D] partials: d(gamma), d(beta), column sum of dx
+  pdl_trigger();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = D / 4;
   float4* sg = reinterpret_cast<float4*>(sm + (size_t)warp * 3 * D);
@@ -139,6 +142,7 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ x, co
     }
   }
 
+  pdl_wait();                     // everything above touched shared memory only
   for (int64_t r = (int64_t)blockIdx.x * LN_WARPS + warp; r < rows; r += (int64_t)gridDim.x * LN_WARPS) {
     const float4* xr = reinterpret_cast<const float4*>(x + r * D);
     const TDY* dyr = dy + r * D;
@@ -216,6 +220,8 @@ __global__ void __launch_bounds__(256)
 layernorm_bwd_final_kernel(const float* __restrict__ ws, int nblocks, int D,
                            float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcolsum) {
   __shared__ float red[8][33];
+  pdl_trigger();
+  pdl_wait();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
   float t = 0.f;
@@ -248,7 +254,7 @@ static int launch_ln_bwd(const TDY* dy, const float* x, const float* gamma, cons
     auto k = layernorm_bwd_kernel<TDY, TLP, NV>;                                                              \
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
     cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);    \
-    k<<<grid, LN_WARPS * 32, smem, s>>>(dy, x, gamma, mean, rstd, dres, dx, dx_lp, ws, want, want_cs, rows, D);  \
+    avj_launch_pdl(k, dim3(grid), dim3(LN_WARPS * 32), smem, s, dy, x, gamma, mean, rstd, dres, dx, dx_lp, ws, want, want_cs, rows, D);  \
   } break;
   switch (nv4) {
     LNB_CASE(1) LNB_CASE(2) LNB_CASE(3) LNB_CASE(4) LNB_CASE(5) LNB_CASE(6) LNB_CASE(7) LNB_CASE(8)
@@ -258,7 +264,7 @@ static int launch_ln_bwd(const TDY* dy, const float* x, const float* gamma, cons
 #undef LNB_CASE
   AVJ_LAUNCH_CHECK();
   if (want || want_cs) {
-    layernorm_bwd_final_kernel<<<(3 * D + 31) / 32, 256, 0, s>>>(ws, grid, D, dgamma, dbeta, dcolsum);
+    avj_launch_pdl(layernorm_bwd_final_kernel, dim3((3 * D + 31) / 32), dim3(256), 0, s, ws, grid, D, dgamma, dbeta, dcolsum);
     AVJ_LAUNCH_CHECK();
   }
   return 0;

@@ -34,12 +34,14 @@
 #define UA_LOADERS 96             // cp.async path: warps 0, 2, 3
 #define UA_P_TILE (128 * 128)                     // one 64-key atom of P: 128 rows x 128 B
 
-// K/V ring depth: the stage of tile t is released by PV(t), so 2 stages expose the full load latency of
-// tile t+2 every step.  hd <= 32 tiles have 64-byte rows (UaTile) and afford 4 stages next to a second CTA.
-template <int HDP> struct UaSmem {
-  static constexpr int NST = HDP == 32 ? 4 : 2;
+// K/V ring depth: the stage of tile t is released by PV(t), so with 2 stages the load of tile t+2 is issued when
+// PV(t) retires and S(t+2) -- wanted one softmax later -- waits out its full L2 latency every tile.  hd <= 32 tiles
+// have 64-byte rows (UaTile) and afford 4 stages next to a second CTA; at hd = 64 there is room for 3 once P lives
+// in tensor memory (TS) and its 32 KB of shared memory are gone.
+template <int HDP, bool TS> struct UaSmem {
+  static constexpr int NST = HDP == 32 ? 4 : (TS ? 3 : 2);
   static constexpr uint32_t TILE = 128 * UaTile<HDP>::PITCH;
-  static constexpr uint32_t Q = 0, K = TILE, V = K + NST * TILE, P = V + NST * TILE, BARS = P + 2 * UA_P_TILE,
+  static constexpr uint32_t Q = 0, K = TILE, V = K + NST * TILE, P = V + NST * TILE, BARS = P + (TS ? 0 : 2 * UA_P_TILE),
                             TOTAL = BARS + 256;
 };
 #define UA_TMEM_COLS 256
@@ -56,7 +58,7 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
                    float* __restrict__ lse, int N, int H, int hd, float scale_log2) {
   extern __shared__ __align__(1024) uint8_t ua_raw[];
   const uint32_t base = ua_smem(ua_raw);
-  using L = UaSmem<HDP>;
+  using L = UaSmem<HDP, TS>;
   using TL = UaTile<HDP>;
   constexpr int NST = L::NST;
   constexpr uint32_t UA_TILE_BYTES = L::TILE;
@@ -214,16 +216,23 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
 #pragma unroll
         for (int j = 0; j < 128; ++j) if (j >= nvalid) s[j] = -INFINITY;
       }
-      float tmax = s[0];
+      // four independent chains (a single running maximum is 64 dependent FMNMX3 ~ 300 idle cycles per tile)
+      float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]), mx2 = fmaxf(s[4], s[5]), mx3 = fmaxf(s[6], s[7]);
 #pragma unroll
-      for (int j = 1; j < 128; ++j) tmax = fmaxf(tmax, s[j]);
+      for (int j = 8; j < 128; j += 8) {
+        mx0 = fmaxf(mx0, fmaxf(s[j], s[j + 1]));
+        mx1 = fmaxf(mx1, fmaxf(s[j + 2], s[j + 3]));
+        mx2 = fmaxf(mx2, fmaxf(s[j + 4], s[j + 5]));
+        mx3 = fmaxf(mx3, fmaxf(s[j + 6], s[j + 7]));
+      }
+      const float tmax = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       const float m_new = fmaxf(m, tmax);
       // lazy rescale: keep the stale maximum unless it is off by more than 2^8
       const bool jump = (m_new - m) * scale_log2 > 8.0f;             // true for t == 0 (m = -inf)
       const float m_use = jump ? m_new : m;
       const float corr = exp2f((m - m_use) * scale_log2);            // 1 when unchanged, 0 at t == 0
       const float mb = m_use * scale_log2;
-      float rsum = 0.f;
+      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
       uint32_t pk[64];
 #pragma unroll
       for (int j = 0; j < 128; j += 2) {
@@ -231,10 +240,13 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
         const bool poly = POLY && ((j >> 1) & 3) == 3;
         const float p0 = poly ? ua_exp2_poly(x0) : ua_exp2(x0);
         const float p1 = poly ? ua_exp2_poly(x1) : ua_exp2(x1);
-        rsum += p0 + p1;
+        if (((j >> 1) & 3) == 0) rs0 += p0 + p1;
+        else if (((j >> 1) & 3) == 1) rs1 += p0 + p1;
+        else if (((j >> 1) & 3) == 2) rs2 += p0 + p1;
+        else rs3 += p0 + p1;
         pk[j >> 1] = pack_bf16x2(p0, p1);
       }
-      l = l * corr + rsum;
+      l = l * corr + ((rs0 + rs1) + (rs2 + rs3));
       m = m_use;
       if (t > 0) ua_mbar_wait(o_done, (t - 1) & 1);                  // PV[t-1] finished: P smem and O are ours
       ua_fence_after();
@@ -352,7 +364,7 @@ template <int HDP, bool TMA, bool POLY, bool TS>
 static int ua_launch(const bf16* qkv, bf16* out, float* lse, int B, int N, int H, int hd, float scale, cudaStream_t s) {
   static bool set = false;
   if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(fa_fwd_umma_kernel<HDP, TMA, POLY, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UaSmem<HDP>::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(fa_fwd_umma_kernel<HDP, TMA, POLY, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UaSmem<HDP, TS>::TOTAL);
     AVJ_CHECK(e == cudaSuccess, "cudaFuncSetAttribute(fa_fwd_umma_kernel) failed: %s", cudaGetErrorString(e));
     // two CTAs per SM need the full 228 KB shared-memory carve-out
     cudaFuncSetAttribute(fa_fwd_umma_kernel<HDP, TMA, POLY, TS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -365,7 +377,7 @@ static int ua_launch(const bf16* qkv, bf16* out, float* lse, int B, int N, int H
     if (rc) return rc;
   }
   dim3 grid((N + UA_BM - 1) / UA_BM, H, B);
-  avj_launch_pdl(fa_fwd_umma_kernel<HDP, TMA, POLY, TS>, grid, dim3(UA_THREADS), UaSmem<HDP>::TOTAL, s, map, qkv, out, lse, N, H, hd, scale * 1.4426950408889634f);
+  avj_launch_pdl(fa_fwd_umma_kernel<HDP, TMA, POLY, TS>, grid, dim3(UA_THREADS), UaSmem<HDP, TS>::TOTAL, s, map, qkv, out, lse, N, H, hd, scale * 1.4426950408889634f);
   AVJ_LAUNCH_CHECK();
   return 0;
 }

@@ -200,15 +200,26 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, const CUtenso
       if (lane == 0) tma_store_2d(map, stg + st_buf * 2048, n0, row_base);
       st_buf = (st_buf + 1) % NBUF;
     };
+    // GELU' operand (the saved pre-activation, thread == row): the loads of step c + 32 are issued before the
+    // math of step c and those of the first step before the tile's MMAs have even retired, so their L2 / HBM
+    // latency never sits on the epilogue's critical path
+    uint4 aux_nxt[4];
+    auto load_aux = [&](int c) {
+      const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.dact_aux) + row * (int64_t)p.N +
+                                                       n_blk * p.block_n + c);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) aux_nxt[j] = row_ok ? __ldg(ap + j) : make_uint4(0u, 0u, 0u, 0u);
+    };
+    if (EPI == EPI_DACT) load_aux(c_lo);
     wait_full();
     tmem_ld32_issue(taddr + c_lo, raw);
     for (int c = c_lo; c < c_hi; c += 32) {
       const int n0 = n_blk * p.block_n + c;
       uint4 aux[4];
       if (EPI == EPI_DACT) {
-        const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.dact_aux) + row * (int64_t)p.N + n0);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) aux[j] = row_ok ? ap[j] : make_uint4(0u, 0u, 0u, 0u);
+        for (int j = 0; j < 4; ++j) aux[j] = aux_nxt[j];
+        if (c + 32 < c_hi) load_aux(c + 32);
       }
       tmem_ld_wait();
       float v[32];

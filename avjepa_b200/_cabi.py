@@ -67,7 +67,8 @@ class Stack(C.Structure):
 
 class StackScratch(C.Structure):
     _fields_ = [('dxa', C.c_void_p), ('dxb', C.c_void_p), ('dx_lp', C.c_void_p), ('d_hid', C.c_void_p),
-                ('d_qkv', C.c_void_p), ('d_h', C.c_void_p), ('d_o', C.c_void_p), ('ws', C.c_void_p)]
+                ('d_qkv', C.c_void_p), ('d_h', C.c_void_p), ('d_o', C.c_void_p), ('ws', C.c_void_p),
+                ('layer_done', C.POINTER(C.c_void_p))]
 
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float

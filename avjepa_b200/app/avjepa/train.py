@@ -96,6 +96,8 @@ class TrainStep(object):
                 loss_reg = avj_loss.reg_value(z)
                 loss = loss_jepa
         # bf16 needs no loss scaling; the scaler object only mirrors the reference call sites
+        if self.grad_sync is not None and hasattr(self.grad_sync, 'begin_step'):
+            self.grad_sync.begin_step(opt, _backbone(self.encoder), len(masks_enc_v), len(masks_enc_v))
         loss.backward()
         if isinstance(opt, FusedAdamWEMA):
             opt.mark_grads_dirty()

@@ -160,7 +160,12 @@ def encoder_backward(mod, st, dout):
     sh = _shadows(mod)
     blocks = [BlockW(b, sh, mode, True) for b in mod.blocks]
     norm = NormW(mod.norm, True) if mod.norm is not None else None
-    dx0 = run.backward(blocks, norm, dout.data_ptr(), F32, sc)
+    from avjepa_b200 import dist as avj_dist
+    sync = avj_dist.active_sync()
+    evs = sync.layer_events_for(mod, run.L) if sync is not None else None
+    dx0 = run.backward(blocks, norm, dout.data_ptr(), F32, sc, layer_events=evs)
+    if evs is not None:
+        sync.on_layers_enqueued(mod, evs)
     pe = mod.patch_embed
     ws = sc.alloc(4 * lib.avj_colsum_ws_floats(B * max(Kv, Ka, 1), D))
     dxc = sc.alloc(B * max(Kv, Ka, 1) * D * s)
@@ -176,6 +181,8 @@ def encoder_backward(mod, st, dout):
         if gw is not None:
             engine.copy_rows(dx0, F32, D, rm, dxc, cd, D, IDENTITY, B * K, D)
             engine.gemm(mode, GEMM_TN, dxc, patches.data_ptr(), gw, D, kd, B * K, D, kd, kd, F32, accumulate=1)
+    if sync is not None:
+        sync.on_backward_done('encoder', mod)
 
 
 class EncoderFn(torch.autograd.Function):
@@ -420,6 +427,10 @@ class PredictorFn(torch.autograd.Function):
         dz_v = dz_a = None
         if dout is not None:
             dz_v, dz_a = predictor_backward(ctx.mod, ctx.parts, ctx.st, dout)
+            from avjepa_b200 import dist as avj_dist
+            sync = avj_dist.active_sync()
+            if sync is not None:
+                sync.on_backward_done('predictor', ctx.mod)
             if dz_a is None and ctx.za_shape is not None and ctx.needs_input_grad[6]:
                 dz_a = torch.zeros(ctx.za_shape, dtype=torch.float32, device=dout.device)
         ctx.st = None

@@ -105,6 +105,9 @@ extern "C" int avj_stack_backward(const avj_stack* s, const avj_layer* L, const 
     RC(avj_layernorm_bwd(sc->d_h, cd, w.x, w.n1.w, w.mean1, w.rstd1, cur, nxt, sc->dx_lp, cd, w.n1.gw, w.n1.gb,
                          i > 0 ? L[i - 1].fc2.gb : nullptr, sc->ws, R, D, stream));
     { float* t = cur; cur = nxt; nxt = t; }
+    // layer i's weight / bias / LayerNorm gradients are complete (fc2.gb of layer i was written by layer i+1)
+    if (sc->layer_done && sc->layer_done[i])
+      AVJ_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(sc->layer_done[i]), as_stream(stream)));
   }
   // two swaps per layer: the result is back in dxa
   return 0;

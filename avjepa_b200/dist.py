@@ -36,14 +36,50 @@ def init_distributed(port=37123, rank_and_world_size=(None, None)):
     return world, rank
 
 
-class GradSync(object):
-    """Averages the optimizer's flat gradient buffers across ranks."""
+_ACTIVE = None
 
-    def __init__(self, world_size, bucket_bytes=64 << 20, group=None):
+
+def active_sync():
+    """The GradSync armed for the step whose backward is running (None outside a data-parallel step)."""
+    return _ACTIVE
+
+
+class GradSync(object):
+    """Averages the optimizer's flat gradient buffers across ranks.
+
+    Plain mode: after backward, every flat buffer is all-reduced (SUM) in bucket-sized chunks.
+
+    Overlapped mode (default with NCCL + the fused optimizer; ``AVJ_DDP_OVERLAP=0`` turns it off): the
+    backward itself reports which gradient ranges are final and their all-reduce starts behind them on a
+    side stream while the rest of the backward still computes --
+
+    * predictor ranges when the last predictor backward of the step has been enqueued (the whole context-
+      encoder backward is still to come),
+    * encoder layers in buckets of ``layers_per_bucket`` while the LAST encoder backward runs: the C schedule
+      (``avj_stack_backward``) records one CUDA event per layer, the side stream waits for the event of the
+      bucket's lowest layer,
+    * whatever is left (patch embedding, final norm, ...) at the end.
+
+    Each range keeps the list of element intervals already reduced, so nothing is reduced twice and
+    ``all_reduce`` finishes the complement.
+    """
+
+    def __init__(self, world_size, bucket_bytes=64 << 20, group=None, overlap=None, layers_per_bucket=4):
         self.world_size = world_size
         self.bucket_elems = bucket_bytes // 4
         self.group = group
+        if overlap is None:
+            overlap = os.environ.get('AVJ_DDP_OVERLAP', '1') != '0'
+        self.overlap = bool(overlap) and torch.cuda.is_available() and world_size > 1
+        self.layers_per_bucket = layers_per_bucket
+        self._side = None
+        self._events = None
+        self._works = []
+        self._done = {}
+        self._left = {}
+        self._enc = self._opt = None
 
+    # ------------------------------------------------------------------ plain path
     def all_reduce_flat(self, flats, average=True):
         """SUM every flat buffer across ranks in bucket-sized chunks.  With average=False the
         caller applies the returned 1/world factor itself (the fused optimizer folds it into its
@@ -65,9 +101,114 @@ class GradSync(object):
             g.mul_(inv)
         return 1.0
 
+    # ------------------------------------------------------------------ overlapped path
+    def begin_step(self, optimizer, encoder_backbone, n_encoder_backward, n_predictor_backward):
+        """Arms the hooks for one backward.  `encoder_backbone`: the module whose `.blocks` the per-layer
+        events refer to; the counts say how many backward calls of each kind this step will make."""
+        global _ACTIVE
+        if not (self.overlap and hasattr(optimizer, '_ranges')):
+            _ACTIVE = None
+            return
+        optimizer.ensure_built()
+        self._opt, self._enc = optimizer, encoder_backbone
+        self._left = {'encoder': int(n_encoder_backward), 'predictor': int(n_predictor_backward)}
+        self._works = []
+        self._done = {id(r['g']): [] for r in optimizer._ranges if r['g'] is not None}
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        _ACTIVE = self
+
+    def _reduce(self, g, lo, hi):
+        """Async SUM of g[lo:hi] (minus what was already reduced), chunked; records the interval."""
+        done = self._done[id(g)]
+        todo, cur = [], lo
+        for a, b in sorted(done):
+            if b <= cur:
+                continue
+            if a >= hi:
+                break
+            if a > cur:
+                todo.append((cur, min(a, hi)))
+            cur = max(cur, b)
+        if cur < hi:
+            todo.append((cur, hi))
+        for a, b in todo:
+            for c0 in range(a, b, self.bucket_elems):
+                c1 = min(b, c0 + self.bucket_elems)
+                self._works.append(tdist.all_reduce(g[c0:c1], op=tdist.ReduceOp.SUM, group=self.group, async_op=True))
+            done.append((a, b))
+
+    def _ranges_of(self, kind):
+        groups = (0, 2) if kind == 'encoder' else (1, 3)
+        return [r for r in self._opt._ranges if r['g'] is not None and r['group'] in groups]
+
+    def _layer_interval(self, r, layers):
+        """[lo, hi) of range r covered by the parameters of encoder layers `layers` (contiguous: the flat
+        order follows module order), or None."""
+        ids = set()
+        for i in layers:
+            ids.update(id(p) for p in self._enc.blocks[i].parameters())
+        lo = hi = None
+        for p, o in zip(r['params'], r['offs']):
+            if id(p) in ids:
+                lo = o if lo is None else min(lo, o)
+                hi = max(hi or 0, o + (p.numel() + 7) // 8 * 8)
+        return None if lo is None else (lo, min(hi, r['g'].numel()))
+
+    def layer_events_for(self, mod, n_layers):
+        """Events for the per-layer hooks of `mod`'s backward -- only for the LAST encoder backward of the step
+        (earlier calls still accumulate into the same gradients)."""
+        if _ACTIVE is not self or mod is not self._enc or self._left.get('encoder', 0) != 1:
+            return None
+        if self._events is None or len(self._events) != n_layers:
+            self._events = [torch.cuda.Event() for _ in range(n_layers)]
+            for e in self._events:
+                e.record()                      # materialise the CUDA handle the C schedule records into
+        return self._events
+
+    def on_layers_enqueued(self, mod, events):
+        """Called right after avj_stack_backward returned (all kernels enqueued, events recorded)."""
+        L = len(events)
+        step = max(1, self.layers_per_bucket)
+        for hi in range(L, 0, -step):
+            layers = range(max(0, hi - step), hi)
+            self._side.wait_event(events[layers[0]])          # the lowest layer of the bucket finishes last
+            with torch.cuda.stream(self._side):
+                for r in self._ranges_of('encoder'):
+                    iv = self._layer_interval(r, layers)
+                    if iv is not None:
+                        self._reduce(r['g'], iv[0], iv[1])
+
+    def on_backward_done(self, kind, mod):
+        if _ACTIVE is not self:
+            return
+        self._left[kind] = self._left.get(kind, 0) - 1
+        if self._left[kind] == 0:
+            for r in self._ranges_of(kind):                   # current stream: everything enqueued so far is ordered before
+                self._reduce(r['g'], 0, r['g'].numel())
+
+    # ------------------------------------------------------------------ entry point after backward
     def all_reduce(self, optimizer, average=True):
+        global _ACTIVE
         if hasattr(optimizer, 'flat_grads'):
             flats = optimizer.flat_grads()
         else:
             flats = [p.grad for grp in optimizer.param_groups for p in grp['params'] if p.grad is not None]
-        return self.all_reduce_flat(flats, average=average)
+        if _ACTIVE is not self:
+            return self.all_reduce_flat(flats, average=average)
+        _ACTIVE = None
+        for g in flats:                                       # the complement of what the hooks already started
+            self._reduce(g, 0, g.numel())
+        for w in self._works:
+            w.wait()
+        self._works = []
+        for g in flats:                                       # every element exactly once
+            iv = sorted(self._done[id(g)])
+            assert iv and iv[0][0] == 0 and iv[-1][1] == g.numel() and all(a[1] == b[0] for a, b in zip(iv, iv[1:])), \
+                'gradient all-reduce coverage error'
+        inv = 1.0 / self.world_size
+        if not average:
+            return inv
+        for g in flats:
+            g.mul_(inv)
+        return 1.0

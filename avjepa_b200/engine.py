@@ -322,9 +322,11 @@ class StackRun(object):
                  _cabi.load().avj_attention_bwd_ws_floats(self.B, self.N, self.H, self.hd)) * 4
         return per + _align(ws) + (1 << 16)
 
-    def backward(self, blocks, norm, dy_ptr, dy_dtype, sc):
+    def backward(self, blocks, norm, dy_ptr, dy_dtype, sc, layer_events=None):
         """dy: gradient wrt LN(x_L) output, [R, D] contiguous in dy_dtype.  `sc` is a scratch
-        Arena with at least scratch_bytes().  Returns the pointer of d x_0 (fp32, in scratch)."""
+        Arena with at least scratch_bytes().  Returns the pointer of d x_0 (fp32, in scratch).
+        `layer_events`: optional list of L torch.cuda.Event; event i is recorded (by the C schedule, on the
+        launch stream) when layer i's parameter gradients are final for this call."""
         assert self.save, 'backward needs a forward run with save=True'
         m, R, D, Hd, cd, s = self.mode, self.R, self.D, self.Hd, self.mode.code, self.mode.size
         scale = float(self.hd ** -0.5)
@@ -347,7 +349,11 @@ class StackRun(object):
             copy_rows(dy_ptr, dy_dtype, D, _cabi.IDENTITY, dx_lp, cd, D, _cabi.IDENTITY, R, D)
         if self.L > 0:
             desc, arr = self._stack_desc(), self._layer_array(blocks)
-            scs = _cabi.StackScratch(cur, nxt, dx_lp, d_hid, d_qkv, d_h, d_o, ws)
+            ev_arr = None
+            if layer_events is not None:
+                assert len(layer_events) == self.L
+                ev_arr = (C.c_void_p * self.L)(*[int(e.cuda_event) for e in layer_events])
+            scs = _cabi.StackScratch(cur, nxt, dx_lp, d_hid, d_qkv, d_h, d_o, ws, ev_arr)
             w0 = blocks[0]
             per_layer = 8 + 2 * sum(1 for g in (w0.fc2.gb, w0.fc1.gb, w0.proj.gb, w0.qkv.gb) if g is not None) \
                 + sum(1 for g in (w0.fc2.gw, w0.fc1.gw, w0.proj.gw, w0.qkv.gw) if g is not None) + 3

@@ -221,6 +221,11 @@ typedef struct avj_stack_scratch {
   void* dx_lp;             /* compute-dtype copy of the current residual gradient (in/out)  */
   void* d_hid; void* d_qkv; void* d_h; void* d_o;
   float* ws;               /* max of the layernorm_bwd / colsum / attention_bwd workspaces  */
+  void* const* layer_done; /* NULL, or L cudaEvent_t handles (NULL entries allowed): event i is
+                              recorded on the stream once every kernel of layer i's backward has
+                              been enqueued, i.e. once layer i's parameter gradients are final for
+                              this call -- the data-parallel host side starts that layer's
+                              gradient all-reduce behind it while lower layers still compute      */
 } avj_stack_scratch;
 int avj_stack_forward(const avj_stack* s, const avj_layer* layers, void* stream);
 int avj_stack_backward(const avj_stack* s, const avj_layer* layers, const avj_stack_scratch* sc, void* stream);

@@ -335,13 +335,15 @@ def main():
     # ---- roofline of the dominant kernel: every GEMM launch of one instrumented step
     peaks = read_peaks()
     roof = None
+    # the library brackets every GEMM / attention / LayerNorm / column-sum / optimizer launch of ONE extra
+    # step with CUDA events on the launch stream (avj_prof_*); nothing is serialised, so the sum per
+    # family is that family's device time inside a normal step.  The step is COLLECTIVE (it contains the
+    # gradient all-reduce), so every rank runs it; only rank 0 instruments and reports.
     if rank == 0:
-        # the library brackets every GEMM / attention / LayerNorm / column-sum / optimizer launch of ONE extra
-        # step with CUDA events on the launch stream (avj_prof_*); nothing is serialised, so the sum per
-        # family is that family's device time inside a normal step.
         _cabi.prof_enable(True)
-        step(host_clips.to(dev), host_asgram.to(dev), *to_device(host_masks[-1]), epoch=0, sync=True)
-        torch.cuda.synchronize()
+    step(host_clips.to(dev), host_asgram.to(dev), *to_device(host_masks[-1]), epoch=0, sync=True)
+    torch.cuda.synchronize()
+    if rank == 0:
         fam = _cabi.prof_collect()
         dump_path = args.prof_dump or os.path.join(tempfile.gettempdir(), f'avj_prof_{os.getpid()}.csv')
         _cabi.prof_dump(dump_path)
@@ -371,11 +373,12 @@ def main():
 
     if world > 1:
         tdist.barrier()
+        tdist.destroy_process_group()
     if rank != 0:
         return
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:        # the CPU baseline is an N = 1 artefact (rank 0 would stall the job)
         cpu, _, _ = cpu_oracle_rate(args.model, args.cpu_sample_batch, 1, 1, budget_s=120.0)
 
     clips_per_s = world * B / (ms_res * 1e-3)

@@ -49,7 +49,7 @@ class GradSync(object):
 
     Plain mode: after backward, every flat buffer is all-reduced (SUM) in bucket-sized chunks.
 
-    Overlapped mode (``AVJ_DDP_OVERLAP=1`` or ``overlap=True``; NCCL + the fused optimizer): the
+    Overlapped mode (default with NCCL + the fused optimizer; ``AVJ_DDP_OVERLAP=0`` turns it off): the
     backward itself reports which gradient ranges are final and their all-reduce starts behind them on a
     side stream while the rest of the backward still computes --
 
@@ -69,7 +69,7 @@ class GradSync(object):
         self.bucket_elems = bucket_bytes // 4
         self.group = group
         if overlap is None:
-            overlap = os.environ.get('AVJ_DDP_OVERLAP', '0') == '1'
+            overlap = os.environ.get('AVJ_DDP_OVERLAP', '1') != '0'
         self.overlap = bool(overlap) and torch.cuda.is_available() and world_size > 1
         self.layers_per_bucket = layers_per_bucket
         self._side = None

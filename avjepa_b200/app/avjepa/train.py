@@ -95,6 +95,11 @@ class TrainStep(object):
             else:
                 loss_reg = avj_loss.reg_value(z)
                 loss = loss_jepa
+        # The loss values exist as soon as the forward has run.  The reference's float(loss) at the end of the
+        # step waits for the whole stream (backward, all-reduce, optimizer) and keeps the host from enqueuing the
+        # next step; here the three scalars cross to pinned host memory on a side stream NOW and the end of the
+        # step only waits for that copy.
+        host_vals = self._stage_losses(loss, loss_jepa, loss_reg) if sync else None
         # bf16 needs no loss scaling; the scaler object only mirrors the reference call sites
         if self.grad_sync is not None and hasattr(self.grad_sync, 'begin_step'):
             self.grad_sync.begin_step(opt, _backbone(self.encoder), len(masks_enc_v), len(masks_enc_v))
@@ -131,7 +136,32 @@ class TrainStep(object):
                          lr=new_lr, wd=new_wd, momentum=m)
         if not sync:
             return loss, loss_jepa, loss_reg, new_lr, new_wd
-        return float(loss), float(loss_jepa), float(loss_reg), new_lr, new_wd
+        if host_vals is None:
+            return float(loss), float(loss_jepa), float(loss_reg), new_lr, new_wd
+        buf, ev = host_vals
+        ev.synchronize()
+        l, lj, lr_ = buf.tolist()
+        return l, lj, lr_, new_lr, new_wd
+
+    def _stage_losses(self, loss, loss_jepa, loss_reg):
+        """Async D2H of (loss, loss_jepa, loss_reg) behind the forward: returns (pinned buffer, event) or None."""
+        if not (torch.is_tensor(loss) and loss.is_cuda):
+            return None
+        dev = loss.device
+        if getattr(self, '_loss_stream', None) is None:
+            self._loss_stream = torch.cuda.Stream(device=dev)
+            self._loss_host = [torch.empty(3, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._loss_events = [torch.cuda.Event() for _ in range(2)]
+            self._loss_slot = 0
+        vals = torch.stack([torch.as_tensor(v, dtype=torch.float32, device=dev).detach().reshape(()) for v in (loss, loss_jepa, loss_reg)])
+        self._loss_slot ^= 1
+        buf, ev = self._loss_host[self._loss_slot], self._loss_events[self._loss_slot]
+        self._loss_stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self._loss_stream):
+            buf.copy_(vals, non_blocking=True)
+            ev.record(self._loss_stream)
+        vals.record_stream(self._loss_stream)
+        return buf, ev
 
 
 def build_training(args, device, world_size=1, rank=0, ipe=None):

@@ -395,7 +395,7 @@ def main():
                     clips_per_s_per_gpu=clips_per_s / world,
                     step_tflops_per_gpu=step_tflops, frac_of_bf16_peak=step_tflops / peaks['bf16_sustained'],
                     flops_per_clip=flops_clip, loss=loss_res),
-        e2e=dict(value=e2e_clips, unit='clips/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
+        e2e=dict(value=e2e_clips, unit='clips/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=12,
                  ms_per_step=ms_e2e, loss=loss_e2e),
         gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu)
     print(json.dumps(line), flush=True)

@@ -72,6 +72,15 @@ def oracle_state(enc, pred, heads):
     return O.StepState(backbone_params(enc), backbone_params(pred), heads=heads)
 
 
+def build_tiny_step(dev, seed=0, mixed=True):
+    """(TrainStep on a seeded ViT-tiny / predictor-depth-2 pair, positional batch tuple for step(*batch))."""
+    clips, asgram, masks, _ = step_inputs()
+    enc, pred = build_product('vit_tiny', seed=seed, device=dev, pred_depth=2)
+    step = make_train_step(enc, pred, mixed)
+    md = to_dev(masks, dev)
+    return step, (clips.to(dev), asgram.to(dev), md['ev'], md['ea'], md['pv'], md['pa'])
+
+
 def run_smoke(dev):
     """__graft_entry__.smoke(): tiny step on cuda:0 in both modes vs the live CPU oracle."""
     from oracle import avjepa_oracle as O

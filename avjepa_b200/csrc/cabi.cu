@@ -74,7 +74,7 @@ extern "C" int avj_prof_dump(const char* path) {
   for (auto& r : g_prof) {
     float e = 0.f;
     if (cudaEventSynchronize(r.b) != cudaSuccess || cudaEventElapsedTime(&e, r.a, r.b) != cudaSuccess) { cudaGetLastError(); continue; }
-    fprintf(f, "%d,%.6g,%.6f,%d,%d,%d,%d\n", r.family, r.work, e, r.d[0], r.d[1], r.d[2], r.d[3]);
+    fprintf(f, "%d,%.12g,%.6f,%d,%d,%d,%d\n", r.family, r.work, e, r.d[0], r.d[1], r.d[2], r.d[3]);
   }
   fclose(f);
   return 0;

@@ -77,7 +77,7 @@ def test_prof_dump_lists_every_launch(tmp_path):
     ln = [r for r in rows if r['family'] == '3']
     assert len(gemm) == 3 and len(ln) == 1 and fam['gemm'][2] == 3 and fam['layernorm_fwd'][2] == 1
     assert all((int(r['d1']), int(r['d2']), int(r['d3'])) == (256, 192, 128) and float(r['ms']) > 0 for r in gemm)
-    assert float(gemm[0]['work']) == 2.0 * 256 * 192 * 128
+    assert float(gemm[0]['work']) == pytest.approx(2.0 * 256 * 192 * 128, rel=1e-5)
     assert (int(ln[0]['d0']), int(ln[0]['d1'])) == (100, 384)
     assert torch.allclose(c.float(), a.float() @ b.float().t(), rtol=2e-2, atol=2e-1)
 
@@ -96,5 +96,5 @@ def test_trainstep_host_read_matches_device_values():
     torch.cuda.synchronize()
     for hs, dv in zip(out_sync[:3], out_dev[:3]):
         assert isinstance(hs, float)
-        assert abs(hs - float(dv)) <= 1e-6 * max(1.0, abs(hs))
+        assert abs(hs - float(dv.detach())) <= 1e-6 * max(1.0, abs(hs))
     assert out_sync[3:] == out_dev[3:]

@@ -118,9 +118,9 @@ class GradSync(object):
             self._side = torch.cuda.Stream()
         _ACTIVE = self
 
-    def _reduce(self, g, lo, hi):
-        """Async SUM of g[lo:hi] (minus what was already reduced), chunked; records the interval."""
-        done = self._done[id(g)]
+    @staticmethod
+    def pending_intervals(done, lo, hi):
+        """Sub-intervals of [lo, hi) not covered by the (possibly unsorted, non-overlapping) intervals in `done`."""
         todo, cur = [], lo
         for a, b in sorted(done):
             if b <= cur:
@@ -132,6 +132,12 @@ class GradSync(object):
             cur = max(cur, b)
         if cur < hi:
             todo.append((cur, hi))
+        return todo
+
+    def _reduce(self, g, lo, hi):
+        """Async SUM of g[lo:hi] (minus what was already reduced), chunked; records the interval."""
+        done = self._done[id(g)]
+        todo = self.pending_intervals(done, lo, hi)
         for a, b in todo:
             for c0 in range(a, b, self.bucket_elems):
                 c1 = min(b, c0 + self.bucket_elems)

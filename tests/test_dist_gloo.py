@@ -41,3 +41,30 @@ def test_grad_sync_world2_gloo(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert 'ok' in o
+
+
+def test_gradsync_pending_intervals_cover_exactly_once():
+    """Bookkeeping of the overlapped all-reduce (dist.GradSync): whatever order the backward reports finished
+    ranges in, every element is reduced exactly once."""
+    import random
+    from avjepa_b200.dist import GradSync
+    rng = random.Random(0)
+    for _ in range(200):
+        n = rng.randint(1, 300)
+        count = [0] * n
+        done = []
+        for _ in range(rng.randint(0, 8)):
+            lo = rng.randint(0, n)
+            hi = rng.randint(lo, n)
+            for a, b in GradSync.pending_intervals(done, lo, hi):
+                assert lo <= a < b <= hi
+                for i in range(a, b):
+                    count[i] += 1
+                done.append((a, b))
+        for a, b in GradSync.pending_intervals(done, 0, n):
+            for i in range(a, b):
+                count[i] += 1
+            done.append((a, b))
+        assert count == [1] * n
+        iv = sorted(done)
+        assert iv[0][0] == 0 and iv[-1][1] == n and all(x[1] == y[0] for x, y in zip(iv, iv[1:]))

@@ -305,7 +305,7 @@ def main():
                 ev0.record()
             if e2e:
                 c, a, m = next(feed)
-                out = step(c, a, *m, epoch=0, sync=os.environ.get('AVJ_E2E_NOSYNC') != '1')   # float(loss): D2H read every step
+                out = step(c, a, *m, epoch=0, sync=True)          # loss scalars read back to the host every step
             else:
                 out = step(clips_d, asgram_d, *dev_masks[i], epoch=0, sync=False)
         ev1.record()

@@ -7,6 +7,7 @@ Fixtures (all small):
   masks_av.npz     AVMaskCollator outputs for a grid of (global seed, batch size, call index)
   masks_video.npz  MaskCollator outputs, same grid
   init_tiny.npz    per-parameter checksums of init_audio_video_model(vit_tiny) under seed 0
+  init_video_tiny.npz  the same for the video-only init_video_model(vit_tiny, predictor depth 6)
   step_tiny.npz    one restated train_step (app/avjepa/train.py:437-537) on ViT-tiny, B=2,
                    seeded synthetic inputs: losses, every parameter-gradient norm, samples of
                    gradients, post-step parameter / target checksums
@@ -183,6 +184,22 @@ def golden_step():
     np.savez_compressed(os.path.join(OUT, 'step_tiny.npz'), **d)
 
 
+def golden_init_video():
+    """init_video_model (app/vjepa/utils.py:86-153) of the video-only twin, vit_tiny, predictor depth 6, seed 0."""
+    from app.vjepa.utils import init_video_model
+    torch.manual_seed(0)
+    np.random.seed(0)
+    enc, pred = init_video_model(
+        device=torch.device('cpu'), patch_size=16, num_frames=16, tubelet_size=2, model_name='vit_tiny', crop_size=224,
+        pred_depth=6, pred_embed_dim=384, uniform_power=True, use_mask_tokens=True, num_mask_tokens=2,
+        zero_init_mask_tokens=True, use_sdpa=True)
+    d = {}
+    for tag, m in (('enc', enc), ('pred', pred)):
+        for n, p in m.named_parameters():
+            d[f'{tag}.{n}'] = checksum(p)
+    np.savez_compressed(os.path.join(OUT, 'init_video_tiny.npz'), **d)
+
+
 def golden_posemb():
     d = {
         'v3d_1024_up': pos_embs.get_3d_sincos_pos_embed(1024, 14, 8, uniform_power=True)[::97, ::13].astype(np.float32),
@@ -199,5 +216,6 @@ if __name__ == '__main__':
     golden_posemb()
     golden_masks()
     golden_init()
+    golden_init_video()
     golden_step()
     print('golden fixtures written to', OUT, 'torch', torch.__version__)

@@ -142,3 +142,27 @@ def test_cpu_tensors_are_rejected():
     from avjepa_b200.src.masks.utils import apply_masks
     with pytest.raises(_cabi.AvjError):
         apply_masks(torch.zeros(1, 4, 8), [torch.zeros(1, 2, dtype=torch.int64)])
+
+
+def test_video_only_init_is_bit_identical_to_reference_init():
+    """init_video_model (app/vjepa/utils.py:86-153): same seed => same 182 parameter tensors as the reference's
+    video-only factory (checksums from the live reference in tests/golden/init_video_tiny.npz)."""
+    import logging
+    logging.disable(logging.CRITICAL)
+    from avjepa_b200.app.vjepa.utils import init_video_model
+    torch.manual_seed(0)
+    np.random.seed(0)
+    enc, pred = init_video_model(
+        device=torch.device('cpu'), patch_size=16, num_frames=16, tubelet_size=2, model_name='vit_tiny', crop_size=224,
+        pred_depth=6, pred_embed_dim=384, uniform_power=True, use_mask_tokens=True, num_mask_tokens=2,
+        zero_init_mask_tokens=True, use_sdpa=True)
+    g = golden('init_video_tiny.npz')
+    names = set()
+    for tag, m in (('enc', enc), ('pred', pred)):
+        for n, p in m.named_parameters():
+            key = f'{tag}.{n}'
+            names.add(key)
+            assert key in g.files, f'parameter {key} does not exist in the reference'
+            assert np.array_equal(checksum(p), g[key]), key
+    assert names == set(g.files)
+    assert enc.backbone.pos_embed.shape == (1, 1568, 192) and pred.backbone.predictor_pos_embed.shape == (1, 1568, 384)

@@ -78,6 +78,7 @@ PROTOTYPES = {
     'avj_version': (_i, []),
     'avj_last_error_string': (C.c_char_p, []),
     'avj_device_ok': (_i, []),
+    'avj_launch_count': (_i64, []),
     'avj_gemm': (_i, [_i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, C.POINTER(Epilogue), _vp]),
     'avj_patchify': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'avj_gather_rows_fwd': (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
@@ -101,6 +102,7 @@ PROTOTYPES = {
     'avj_sumsq_ws_floats': (_i64, [_i64]),
     'avj_sumsq': (_i, [_vp, _i64, _vp, _vp, _vp]),
     'avj_clip_coef': (_i, [_vp, _f, _f, _vp, _vp]),
+    'avj_segment_stats': (_i, [_vp, _vp, _i, _i64, _i, _vp, _vp]),
     'avj_cast': (_i, [_vp, _vp, _i, _i64, _vp]),
     'avj_memset_zero': (_i, [_vp, _i64, _vp]),
     'avj_prof_enable': (_i, [_i]),
@@ -144,16 +146,14 @@ def check(rc, what):
         raise AvjError(f'{what} failed (rc={rc}): {msg.decode() if msg else "?"}')
 
 
-# launch counter: bench.py reports how many of OUR kernels-launching calls ran in the timed region
-launch_count = 0
+def launch_count():
+    """Kernels launched by the library in this process so far -- counted inside the library at every launch site
+    (``AVJ_LAUNCH_CHECK``), not estimated; bench.py reports the difference over its timed region."""
+    return int(load().avj_launch_count())
 
 
-def call(name, *args, launches=1):
-    """`launches`: how many kernels the entry point issues (whole-stack schedules issue many)."""
-    global launch_count
-    lib = load()
-    launch_count += launches
-    check(getattr(lib, name)(*args), name)
+def call(name, *args):
+    check(getattr(load(), name)(*args), name)
 
 
 PROF_FAMILIES = ('gemm', 'attention_fwd', 'attention_bwd', 'layernorm_fwd', 'layernorm_bwd', 'colsum', 'optimizer', 'other')

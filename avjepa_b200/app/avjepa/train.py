@@ -29,7 +29,8 @@ from avjepa_b200.app.avjepa.utils import init_audio_video_model, init_opt, load_
 from avjepa_b200.backbone import _shadows
 from avjepa_b200.optim import FusedAdamWEMA
 from avjepa_b200.src.masks.avmultiblock3d import AVMaskCollator as AVMB3DMaskCollator
-from avjepa_b200.src.utils.logging import AverageMeter, CSVLogger, get_logger, gpu_timer
+from avjepa_b200.src.utils.distributed import AllReduce
+from avjepa_b200.src.utils.logging import AverageMeter, CSVLogger, DeviceParamStats, get_logger, gpu_timer
 
 _GLOBAL_SEED = 0
 log_freq = 10
@@ -48,13 +49,17 @@ class TrainStep(object):
 
     def __init__(self, encoder, predictor, target_encoder, optimizer, scaler, scheduler, wd_scheduler,
                  momentum_scheduler, loss_exp=1.0, reg_coeff=0.0, clip_grad=None, warmup=40,
-                 mixed_precision=True, dtype=torch.bfloat16, grad_sync=None, n_video_tokens=None):
+                 mixed_precision=True, dtype=torch.bfloat16, grad_sync=None, n_video_tokens=None, smooth_l1_beta=None):
         self.encoder, self.predictor, self.target_encoder = encoder, predictor, target_encoder
         self.optimizer, self.scaler = optimizer, scaler
         self.scheduler, self.wd_scheduler, self.momentum_scheduler = scheduler, wd_scheduler, momentum_scheduler
         self.loss_exp, self.reg_coeff, self.clip_grad, self.warmup = loss_exp, reg_coeff, clip_grad, warmup
         self.mixed_precision, self.dtype = mixed_precision, dtype
         self.grad_sync = grad_sync
+        self.smooth_l1_beta = smooth_l1_beta      # None: the reference's |z-h|^p / p;  float: smooth-L1 with this beta
+        self.param_stats = DeviceParamStats()
+        self.keep_zh, self.last_zh = False, None
+        self.stats = None
         for p in target_encoder.parameters():
             p.requires_grad = False
         if isinstance(optimizer, FusedAdamWEMA):
@@ -81,39 +86,57 @@ class TrainStep(object):
             z_t.append((zi[:, :kv], zi[:, kv:]))
         return self.predictor(z_t, [None] * len(z_t), masks_enc, masks_pred)
 
-    def __call__(self, clips, asgram, masks_enc_v, masks_enc_a, masks_pred_v, masks_pred_a, epoch=0, sync=True):
-        new_lr = self.scheduler.step()
-        new_wd = self.wd_scheduler.step()
-        opt = self.optimizer
+    def forward_loss(self, clips, asgram, masks_enc_v, masks_enc_a, masks_pred_v, masks_pred_a):
+        """Step 1 of the reference closure (``:500-509``): (loss, loss_jepa, loss_reg) as device scalars."""
         with torch.autocast('cuda', dtype=self.dtype, enabled=self.mixed_precision):
             h = self.forward_target(clips, asgram, masks_pred_v, masks_pred_a)
             z = self.forward_context(clips, asgram, masks_enc_v, masks_enc_a, masks_pred_v, masks_pred_a)
-            loss_jepa = avj_loss.jepa_loss(z, h, self.loss_exp, unit_grad=(self.reg_coeff == 0.0))
+            loss_jepa = avj_loss.jepa_loss(z, h, self.loss_exp, smooth_l1_beta=self.smooth_l1_beta,
+                                           unit_grad=(self.reg_coeff == 0.0))
             if self.reg_coeff != 0.0:
                 loss_reg = avj_loss.reg_loss_differentiable(z)
                 loss = loss_jepa + self.reg_coeff * loss_reg
             else:
                 loss_reg = avj_loss.reg_value(z)
                 loss = loss_jepa
-        # The loss values exist as soon as the forward has run.  The reference's float(loss) at the end of the
-        # step waits for the whole stream (backward, all-reduce, optimizer) and keeps the host from enqueuing the
-        # next step; here the three scalars cross to pinned host memory on a side stream NOW and the end of the
-        # step only waits for that copy.
-        host_vals = self._stage_losses(loss, loss_jepa, loss_reg) if sync else None
-        # bf16 needs no loss scaling; the scaler object only mirrors the reference call sites
+        if self.keep_zh:               # tests / parity probes only: predictions and targets of this step
+            self.last_zh = ([t.detach() for t in z], h)
+        return loss, loss_jepa, loss_reg
+
+    def backward_and_reduce(self, loss, n_masks=2):
+        """Backward, then (data parallel) the SUM all-reduce of the flat gradient buffers -- overlapped with the
+        backward when the GradSync supports it.  Returns the factor still owed to the gradients (1/world when the
+        fused optimizer folds the averaging into its gradient multiplier, else 1.0).  bf16 needs no loss scaling
+        (LossScaler is the identity); the scaler object only mirrors the reference call sites."""
+        opt = self.optimizer
         if self.grad_sync is not None and hasattr(self.grad_sync, 'begin_step'):
-            self.grad_sync.begin_step(opt, _backbone(self.encoder), len(masks_enc_v), len(masks_enc_v))
+            self.grad_sync.begin_step(opt, _backbone(self.encoder), n_masks, n_masks)
         loss.backward()
-        if isinstance(opt, FusedAdamWEMA):
-            opt.mark_grads_dirty()
-        # data parallel: ranks SUM their flat gradient buffers; the 1/world averaging is folded into
-        # the gradient multiplier the optimizer kernel applies anyway (no extra pass over the grads)
-        inv = 1.0
-        if self.grad_sync is not None:
-            inv = self.grad_sync.all_reduce(opt, average=not isinstance(opt, FusedAdamWEMA))
+        if self.grad_sync is None:
+            return 1.0
+        return self.grad_sync.all_reduce(opt, average=not isinstance(opt, FusedAdamWEMA))
+
+    def __call__(self, clips, asgram, masks_enc_v, masks_enc_a, masks_pred_v, masks_pred_a, epoch=0, sync=True,
+                 log_stats=False):
+        """One iteration.  Returns ``(loss, loss_jepa, loss_reg, lr, wd)`` like the reference closure's first five
+        values (floats when `sync`, device scalars otherwise).  With `log_stats` the per-parameter gradient-norm /
+        Adam-moment statistics of ``grad_logger`` / ``adamw_logger`` (``app/avjepa/train.py:526-531``) are computed
+        on the device as well and left in ``self.stats`` = (enc grad stats, pred grad stats, optim stats)."""
+        new_lr = self.scheduler.step()
+        new_wd = self.wd_scheduler.step()
+        opt = self.optimizer
+        fused = isinstance(opt, FusedAdamWEMA)
+        loss, loss_jepa, loss_reg = self.forward_loss(clips, asgram, masks_enc_v, masks_enc_a, masks_pred_v, masks_pred_a)
+        # The loss values exist as soon as the forward has run.  The reference's float(loss) at the end of the step
+        # waits for the whole stream (backward, all-reduce, optimizer) and keeps the host from enqueuing the next
+        # step; here the three scalars cross to pinned host memory on a side stream NOW and the end of the step only
+        # waits for that copy (unless gradient norms / parameter statistics, which exist only after backward, were
+        # asked for as well).
+        early = self._stage(0, [loss, loss_jepa, loss_reg]) if sync else None
+        inv = self.backward_and_reduce(loss, n_masks=len(masks_enc_v))
         enc_norm = pred_norm = None
         coef = None
-        if isinstance(opt, FusedAdamWEMA) and (epoch > self.warmup) and (self.clip_grad is not None):
+        if fused and (epoch > self.warmup) and (self.clip_grad is not None):         # train.py:518-520
             enc_sq = opt.grad_norm_sq(lambda r: r['group'] in (0, 2))
             pred_sq = opt.grad_norm_sq(lambda r: r['group'] in (1, 3))
             ce, cp = torch.empty_like(enc_sq), torch.empty_like(pred_sq)
@@ -122,10 +145,16 @@ class TrainStep(object):
             _cabi.call('avj_clip_coef', pred_sq.data_ptr(), float(self.clip_grad), inv, cp.data_ptr(), engine.stream())
             coef = {0: ce, 2: ce, 1: cp, 3: cp}
             enc_norm, pred_norm = enc_sq.sqrt() * inv, pred_sq.sqrt() * inv
+        elif (not fused) and (epoch > self.warmup) and (self.clip_grad is not None):
+            enc_norm = torch.nn.utils.clip_grad_norm_(self.encoder.parameters(), self.clip_grad)
+            pred_norm = torch.nn.utils.clip_grad_norm_(self.predictor.parameters(), self.clip_grad)
         m = next(self.momentum_scheduler)
-        if isinstance(opt, FusedAdamWEMA):
-            opt.step(ema_momentum=m, coef_by_group=coef, inv_loss_scale=inv)
-            opt.zero_grad()
+        if fused:
+            if log_stats:
+                self.param_stats.capture_grads(opt, coef, scale=inv)     # before the kernel below zeroes them
+            opt.step(ema_momentum=m, coef_by_group=coef, inv_loss_scale=inv, zero_grads=True)
+            if log_stats:
+                self.param_stats.capture_moments(opt)
         else:       # stock optimizer: unfused EMA, reference order
             opt.step()
             opt.zero_grad()
@@ -136,31 +165,47 @@ class TrainStep(object):
                          lr=new_lr, wd=new_wd, momentum=m)
         if not sync:
             return loss, loss_jepa, loss_reg, new_lr, new_wd
-        if host_vals is None:
-            return float(loss), float(loss_jepa), float(loss_reg), new_lr, new_wd
-        buf, ev = host_vals
+        buf, ev = early
         ev.synchronize()
         l, lj, lr_ = buf.tolist()
+        want_norms = enc_norm is not None
+        self.stats = None
+        if want_norms or (fused and log_stats):
+            # the two global gradient norms and (with log_stats) the per-parameter statistics exist only after the
+            # backward: ONE more asynchronous copy carries all of them (the reference blocks on float(norm) x2 and
+            # ~1000 per-parameter float() calls here)
+            zero = torch.zeros((), dtype=torch.float64, device=loss.device)
+            if not (fused and log_stats):
+                self.param_stats._g = self.param_stats._m = self.param_stats._v = None
+            self.param_stats.stage(self._copy_stream, extra=[enc_norm if want_norms else zero, pred_norm if want_norms else zero])
+            enc_stats, pred_stats, optim_stats, (en, pn) = self.param_stats.collect(
+                list(self.encoder.named_parameters()), list(self.predictor.named_parameters()))
+            self.last.update(enc_norm=en, pred_norm=pn)
+            if log_stats:
+                enc_stats.global_norm, pred_stats.global_norm = en, pn
+                self.stats = (enc_stats, pred_stats, optim_stats)
         return l, lj, lr_, new_lr, new_wd
 
-    def _stage_losses(self, loss, loss_jepa, loss_reg):
-        """Async D2H of (loss, loss_jepa, loss_reg) behind the forward: returns (pinned buffer, event) or None."""
-        if not (torch.is_tensor(loss) and loss.is_cuda):
-            return None
-        dev = loss.device
-        if getattr(self, '_loss_stream', None) is None:
-            self._loss_stream = torch.cuda.Stream(device=dev)
-            self._loss_host = [torch.empty(3, dtype=torch.float32).pin_memory() for _ in range(2)]
-            self._loss_events = [torch.cuda.Event() for _ in range(2)]
-            self._loss_slot = 0
-        vals = torch.stack([torch.as_tensor(v, dtype=torch.float32, device=dev).detach().reshape(()) for v in (loss, loss_jepa, loss_reg)])
-        self._loss_slot ^= 1
-        buf, ev = self._loss_host[self._loss_slot], self._loss_events[self._loss_slot]
-        self._loss_stream.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(self._loss_stream):
+
+    def _stage(self, slot, values):
+        """Asynchronous D2H of a few device scalars on the copy stream: returns (pinned fp32 buffer, event)."""
+        dev = values[0].device if torch.is_tensor(values[0]) else torch.device('cuda', torch.cuda.current_device())
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._slots = {}
+        key = (slot, len(values))
+        if key not in self._slots:
+            self._slots[key] = [[torch.empty(len(values), dtype=torch.float32).pin_memory(), torch.cuda.Event()] for _ in range(2)]
+            self._slots[key].append(0)
+        ring = self._slots[key]
+        ring[2] ^= 1
+        buf, ev = ring[ring[2]]
+        vals = torch.stack([torch.as_tensor(v, dtype=torch.float32, device=dev).detach().reshape(()) for v in values])
+        self._copy_stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self._copy_stream):
             buf.copy_(vals, non_blocking=True)
-            ev.record(self._loss_stream)
-        vals.record_stream(self._loss_stream)
+            ev.record(self._copy_stream)
+        vals.record_stream(self._copy_stream)
         return buf, ev
 
 
@@ -212,14 +257,19 @@ def build_training(args, device, world_size=1, rank=0, ipe=None):
     return step, collator, dict(ipe=ipe, num_epochs=num_epochs, batch_size=data.get('batch_size'))
 
 
-def save_checkpoint(path, step, epoch, loss, batch_size, world_size, lr):
-    """Same dict as the reference (``:332-350``), keys included."""
+def save_checkpoint(path, step, epoch, loss, batch_size, world_size, lr, reference_keys=False):
+    """Same dict as the reference (``:332-350``), keys included.  `reference_keys`: write the model state dicts with
+    the ``module.`` prefix the reference's ``nn.DataParallel`` wrappers produce, so the reference's own (strict)
+    ``load_checkpoint`` reads the file; :func:`load_checkpoint` here reads either form."""
+    def sd(m):
+        d = m.state_dict()
+        return {('module.' + k if reference_keys and not k.startswith('module.') else k): v for k, v in d.items()}
     torch.save({
-        'encoder': step.encoder.state_dict(),
-        'predictor': step.predictor.state_dict(),
+        'encoder': sd(step.encoder),
+        'predictor': sd(step.predictor),
         'opt': step.optimizer.state_dict(),
         'scaler': None if step.scaler is None else step.scaler.state_dict(),
-        'target_encoder': step.target_encoder.state_dict(),
+        'target_encoder': sd(step.target_encoder),
         'epoch': epoch, 'loss': loss, 'batch_size': batch_size, 'world_size': world_size, 'lr': lr,
     }, path)
 
@@ -231,9 +281,13 @@ def synthetic_batch(batch_size, generator=None):
 
 
 def main(args, resume_preempt=False):
+    """The reference loop (``app/avjepa/train.py:68-644``) around :class:`TrainStep`: YAML dict in, CSV rows and
+    ``<tag>-latest.pth.tar`` out, resume from ``meta.load_checkpoint`` / ``meta.read_checkpoint`` or an existing
+    latest checkpoint with the schedulers, momentum generator and mask collator fast-forwarded (``:309-330``)."""
     world_size, rank = avj_dist.init_distributed()
     device = torch.device('cuda', torch.cuda.current_device())
     step, collator, info = build_training(args, device, world_size, rank)
+    meta = args.get('meta')
     folder, tag = args.get('logging').get('folder'), args.get('logging').get('write_tag')
     os.makedirs(folder, exist_ok=True)
     csv_logger = CSVLogger(os.path.join(folder, f'{tag}_r{rank}.csv'), ('%d', 'epoch'), ('%d', 'itr'), ('%.5f', 'loss'),
@@ -244,25 +298,80 @@ def main(args, resume_preempt=False):
         raise NotImplementedError('only data.dataset_type == "synthetic" is available: the decord/ffmpeg/librosa data '
                                   'pipeline of the reference is outside this package (SURVEY.md section 2, row 14)')
     ipe, num_epochs, B = info['ipe'], info['num_epochs'], info['batch_size']
-    for epoch in range(num_epochs):
-        loss_meter = AverageMeter()
+
+    # -- resume (reference :187-193, :309-330)
+    load_model = bool(meta.get('load_checkpoint', False)) or resume_preempt
+    r_file = meta.get('read_checkpoint', None)
+    load_path = None
+    if load_model:
+        load_path = os.path.join(folder, r_file) if r_file is not None else latest_path
+        if not os.path.exists(load_path):
+            load_path, load_model = None, False
+    start_epoch = 0
+    if load_model or os.path.exists(latest_path):
+        logger.info('LOADING CHECKPOINTS')
+        *_, start_epoch = load_checkpoint(r_path=load_path or latest_path, encoder=step.encoder, predictor=step.predictor,
+                                          target_encoder=step.target_encoder, opt=step.optimizer, scaler=step.scaler)
+        for _ in range(start_epoch * ipe):
+            step.scheduler.step()
+            step.wd_scheduler.step()
+            next(step.momentum_scheduler)
+            collator.step()
+
+    # every rank draws its own clips (the reference shards the dataset with a DistributedSampler)
+    data_gen = torch.Generator().manual_seed(int(meta.get('seed', _GLOBAL_SEED)) * 1000003 + rank)
+    new_lr = new_wd = 0.
+    for epoch in range(start_epoch, num_epochs):
+        loss_meter, input_var_meter, input_var_min_meter = AverageMeter(), AverageMeter(), AverageMeter()
+        jepa_loss_meter, reg_loss_meter = AverageMeter(), AverageMeter()
+        gpu_time_meter, wall_time_meter = AverageMeter(), AverageMeter()
+        mask_meters = [AverageMeter() for _ in range(len(args.get('mask')))]
         for itr in range(ipe):
             t0 = time.time()
             while True:
                 try:
-                    udata, me_v, me_a, mp_v, mp_a = collator(synthetic_batch(B))
+                    udata, me_v, me_a, mp_v, mp_a = collator(synthetic_batch(B, data_gen))
                     break
                 except TypeError:      # the reference collator's 0-d crash: resample
                     continue
             clips = torch.cat([u.to(device, non_blocking=True) for u in udata[0]], dim=0)
             asgram = udata[3].unsqueeze(1).to(device, non_blocking=True)
             mv = [[m.to(device, non_blocking=True) for m in ms] for ms in (me_v, me_a, mp_v, mp_a)]
-            (loss, lj, lr_, new_lr, new_wd), gpu_ms = gpu_timer(lambda: step(clips, asgram, *mv, epoch=epoch))
+            for i, mm in enumerate(mask_meters):
+                mm.update(me_v[i][0].size(-1))
+            want_stats = (itr % log_freq == 0)
+            (loss, lj, lr_, new_lr, new_wd), gpu_ms = gpu_timer(
+                lambda: step(clips, asgram, *mv, epoch=epoch, log_stats=want_stats))
+            wall_ms = (time.time() - t0) * 1000.
             loss_meter.update(loss)
-            csv_logger.log(epoch + 1, itr, loss, lj, lr_, 0., 0., gpu_ms, (time.time() - t0) * 1000.)
-            if itr % log_freq == 0:
-                logger.info('[%d, %5d] loss: %.3f [wd: %.2e] [lr: %.2e] [gpu: %.1f ms]' %
-                            (epoch + 1, itr, loss_meter.avg, new_wd, new_lr, gpu_ms))
+            # the two logging collectives of the reference (:560-561)
+            per_clip_var = clips.view(clips.shape[0], -1).var(dim=1)
+            input_var = float(AllReduce.apply(per_clip_var.mean(dim=0)))
+            input_var_min = float(AllReduce.apply(torch.min(per_clip_var)))
+            input_var_meter.update(input_var)
+            input_var_min_meter.update(input_var_min)
+            jepa_loss_meter.update(lj)
+            reg_loss_meter.update(lr_)
+            gpu_time_meter.update(gpu_ms)
+            wall_time_meter.update(wall_ms)
+            enc_norm, pred_norm = step.last.get('enc_norm') or 0., step.last.get('pred_norm') or 0.
+            csv_logger.log(epoch + 1, itr, loss, lj, lr_, enc_norm, pred_norm, gpu_ms, wall_ms)
+            if want_stats or np.isnan(loss) or np.isinf(loss):
+                logger.info('[%d, %5d] loss: %.3f | p%.3f r%.3f | input_var: %.3f %.3f | masks: %s [wd: %.2e] [lr: %.2e] '
+                            '[mem: %.2e] [gpu: %.1f ms][wall: %.1f ms]'
+                            % (epoch + 1, itr, loss_meter.avg, jepa_loss_meter.avg, reg_loss_meter.avg, input_var_meter.avg,
+                               input_var_min_meter.avg, '[' + ', '.join('%.1f' % m.avg for m in mask_meters) + ']',
+                               new_wd, new_lr, torch.cuda.max_memory_allocated() / 1024.0 ** 2, gpu_time_meter.avg,
+                               wall_time_meter.avg))
+                if step.stats is not None:
+                    g_enc, g_pred, o = step.stats
+                    logger.info('[%d, %5d] first moment: %.2e [%.2e %.2e] second moment: %.2e [%.2e %.2e]'
+                                % (epoch + 1, itr, o['exp_avg'].avg, o['exp_avg'].min, o['exp_avg'].max,
+                                   o['exp_avg_sq'].avg, o['exp_avg_sq'].min, o['exp_avg_sq'].max))
+                    for nm, g in (('enc', g_enc), ('pred', g_pred)):
+                        logger.info('[%d, %5d] %s_grad_stats: f/l[%.2e %.2e] mn/mx(%.2e, %.2e) %.2e'
+                                    % (epoch + 1, itr, nm, g.first_layer, g.last_layer, g.min, g.max, g.global_norm))
             assert not np.isnan(loss), 'loss is nan'
+        logger.info('avg. loss %.3f' % loss_meter.avg)
         if rank == 0 and (epoch % checkpoint_freq == 0 or epoch == num_epochs - 1):
             save_checkpoint(latest_path, step, epoch + 1, loss_meter.avg, B, world_size, new_lr)

@@ -91,13 +91,15 @@ def init_audio_video_model(
 
 
 class LossScaler(object):
-    """Constant-free stand-in for ``torch.cuda.amp.GradScaler`` (reference ``init_opt`` returns one
-    even for bf16, ``app/avjepa/utils.py:281``).  bf16 has fp32's exponent range, so scaling by
-    2^16 and unscaling is an exact no-op; this object keeps the call sites
-    (``scale / unscale_ / step / update / state_dict``) working without the per-parameter
-    inf-check syncs, and folds the unscale into the fused AdamW kernel."""
+    """Stand-in for ``torch.cuda.amp.GradScaler`` (the reference's ``init_opt`` returns one even for bf16,
+    ``app/avjepa/utils.py:281``).  bf16 has fp32's exponent range, so no loss scaling is needed: the scale is the
+    constant 1.0, ``scale(loss)`` returns the loss itself and ``unscale_`` has nothing to undo -- which keeps the
+    reference's call order ``scale -> backward -> unscale_ -> clip_grad_norm_ -> step -> update``
+    (``app/avjepa/train.py:514-523``) exact: clipping between ``unscale_`` and ``step`` sees the true gradients.
+    No per-parameter inf-check syncs are issued.  A scale other than 1 (``update(new_scale=...)``) is honoured
+    faithfully: ``unscale_`` then divides the optimizer's gradients once, like GradScaler does."""
 
-    def __init__(self, init_scale=65536.0, enabled=True):
+    def __init__(self, init_scale=1.0, enabled=True):
         self._scale = float(init_scale)
         self._enabled = enabled
         self._unscaled = False
@@ -106,27 +108,35 @@ class LossScaler(object):
         return self._enabled
 
     def get_scale(self):
-        return self._scale
+        return self._scale if self._enabled else 1.0
 
     def scale(self, loss):
-        return loss * self._scale if self._enabled else loss
+        if not self._enabled or self._scale == 1.0:
+            return loss
+        return loss * self._scale
 
     def unscale_(self, optimizer):
-        self._unscaled = True       # folded into the optimizer kernel (see step)
-
-    def step(self, optimizer, *args, **kwargs):
-        inv = 1.0 / self._scale if self._enabled else 1.0
-        self._unscaled = False
+        if self._unscaled:
+            raise RuntimeError('unscale_() has already been called on this optimizer since the last update().')
+        self._unscaled = True
+        if not self._enabled or self._scale == 1.0:
+            return
+        inv = 1.0 / self._scale
         if isinstance(optimizer, FusedAdamWEMA):
-            return optimizer.step(*args, inv_loss_scale=inv, **kwargs)
-        if inv != 1.0:
+            optimizer.scale_grads(inv)
+        else:
             for g in optimizer.param_groups:
                 for p in g['params']:
                     if p.grad is not None:
                         p.grad.mul_(inv)
+
+    def step(self, optimizer, *args, **kwargs):
+        if not self._unscaled:
+            self.unscale_(optimizer)
         return optimizer.step(*args, **kwargs)
 
     def update(self, new_scale=None):
+        self._unscaled = False
         if new_scale is not None:
             self._scale = float(new_scale)
 
@@ -135,7 +145,9 @@ class LossScaler(object):
                 '_growth_tracker': 0}
 
     def load_state_dict(self, sd):
-        self._scale = float(sd.get('scale', self._scale))
+        """The dynamic scale of a reference checkpoint (2^16 and up) is an artefact of running GradScaler on bf16;
+        it carries no training state, so it is NOT adopted -- the scale stays 1."""
+        return None
 
 
 def init_opt(
@@ -195,25 +207,45 @@ def init_opt(
     return optimizer, scaler, scheduler, wd_scheduler
 
 
+def _strip_module(sd):
+    return {(k[len('module.'):] if k.startswith('module.') else k): v for k, v in sd.items()}
+
+
+def _match_keys(module, sd):
+    """Reference checkpoints are written from ``nn.DataParallel`` wrappers (``app/avjepa/train.py:298-300,332-350``),
+    so their keys are ``module.backbone.*``; this package's modules expose ``backbone.*``.  Re-key `sd` to whatever
+    `module` itself uses (works in both directions)."""
+    own = list(module.state_dict().keys())
+    wants_prefix = bool(own) and all(k.startswith('module.') for k in own)
+    sd = _strip_module(sd)
+    if wants_prefix:
+        sd = {'module.' + k: v for k, v in sd.items()}
+    return sd
+
+
 def load_checkpoint(r_path, encoder, predictor, target_encoder, opt, scaler):
-    """Reads a checkpoint written by either implementation (same keys: encoder, predictor,
-    target_encoder, opt, scaler, epoch).  Errors are logged and swallowed like the reference."""
+    """Reads a checkpoint written by this package OR by the reference (``app/avjepa/utils.py:28-83``): same
+    top-level keys (encoder, predictor, target_encoder, opt, scaler, epoch); the ``module.`` prefix that the
+    reference's DataParallel wrappers add is normalised away.  Like the reference, a checkpoint that cannot be
+    READ (missing / truncated file) is logged and training starts from epoch 0; a checkpoint whose parameter
+    names or shapes do not match the models is an ERROR -- silently restarting from random init would be wrong."""
     epoch = 0
     try:
         checkpoint = torch.load(r_path, map_location=torch.device('cpu'))
-        epoch = checkpoint['epoch']
-        for name, module in (('encoder', encoder), ('predictor', predictor), ('target_encoder', target_encoder)):
-            if module is None:
-                continue
-            msg = module.load_state_dict(checkpoint[name])
-            logger.info(f'loaded pretrained {name} from epoch {epoch} with msg: {msg}')
-        opt.load_state_dict(checkpoint['opt'])
-        if scaler is not None:
-            scaler.load_state_dict(checkpoint['scaler'])
-        logger.info(f'loaded optimizers from epoch {epoch}')
-        logger.info(f'read-path: {r_path}')
-        del checkpoint
     except Exception as e:
         logger.info(f'Encountered exception when loading checkpoint {e}')
-        epoch = 0
+        return encoder, predictor, target_encoder, opt, scaler, epoch
+    epoch = checkpoint['epoch']
+    for name, module in (('encoder', encoder), ('predictor', predictor), ('target_encoder', target_encoder)):
+        if module is None:
+            continue
+        msg = module.load_state_dict(_match_keys(module, checkpoint[name]))      # strict: raises on a mismatch
+        logger.info(f'loaded pretrained {name} from epoch {epoch} with msg: {msg}')
+    if opt is not None and checkpoint.get('opt') is not None:
+        opt.load_state_dict(checkpoint['opt'])
+    if scaler is not None and checkpoint.get('scaler') is not None:
+        scaler.load_state_dict(checkpoint['scaler'])
+    logger.info(f'loaded optimizers from epoch {epoch}')
+    logger.info(f'read-path: {r_path}')
+    del checkpoint
     return encoder, predictor, target_encoder, opt, scaler, epoch

@@ -298,6 +298,7 @@ static int bwd_launch(const T* qkv, const T* out, const T* dout, const float* ls
       cudaFuncSetAttribute(attn_bwd_dkv_simt<T, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dkv); \
     }                                                                                                             \
     attn_bwd_dq_simt<T, ND><<<grid, AT_WARPS * 32, smem_dq, s>>>(qkv, dout, lse, delta, dqkv, B, N, H, hd, scale);   \
+    AVJ_COUNT_LAUNCH();                                                                                             \
     attn_bwd_dkv_simt<T, ND><<<grid, AT_WARPS * 32, smem_dkv, s>>>(qkv, dout, lse, delta, dqkv, B, N, H, hd, scale); \
     break;
   switch (nd) { BWD_CASE(1) BWD_CASE(2) BWD_CASE(3) BWD_CASE(4)

@@ -13,6 +13,10 @@ bool avj_pdl_enabled() {
   return v == 1;
 }
 
+// ---- launch counter (AVJ_LAUNCH_CHECK feeds it) ------------------------------------------------
+unsigned long long g_avj_launches = 0;
+extern "C" int64_t avj_launch_count(void) { return (int64_t)__atomic_load_n(&g_avj_launches, __ATOMIC_RELAXED); }
+
 // ---- kernel timing ---------------------------------------------------------------------------
 bool g_avj_prof_on = false;
 namespace {
@@ -118,6 +122,13 @@ static bool force_simt() {
   if (v < 0) { const char* e = getenv("AVJ_FORCE_SIMT"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
 }
+// AVJ_GEMM_SIMT_FALLBACK=1 lets a bf16 GEMM the tcgen05 kernel refuses run on the fp32-FMA check kernel
+// (~100x slower); by default such a call is an ERROR so that a mis-shaped production call cannot hide.
+static bool allow_simt_fallback() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("AVJ_GEMM_SIMT_FALLBACK"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
 static bool force_simt_attn() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("AVJ_FORCE_SIMT_ATTN"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -142,6 +153,11 @@ extern "C" int avj_gemm(int dtype, int layout, const void* A, const void* B, voi
   AvjProfScope prof(AVJ_FAM_GEMM, 2.0 * M * (double)N * K, stream, epi_bits, M, N, K);
   if (!force_simt() && avj_gemm_umma_supported(dtype, layout, A, B, M, N, K, lda, ldb, ep))
     return avj_gemm_umma(layout, A, B, C, M, N, K, lda, ldb, ldc, ep, as_stream(stream));
+  AVJ_CHECK(dtype == AVJ_F32 || force_simt() || allow_simt_fallback(),
+            "avj_gemm: bf16 problem not supported by the tcgen05 kernel (layout=%d M=%d N=%d K=%d lda=%d ldb=%d A%%16=%d B%%16=%d; "
+            "needs N %% 64 == 0, lda/ldb %% 8 == 0, 16-byte aligned A/B, and M %% 8 == 0 for TN). Set AVJ_GEMM_SIMT_FALLBACK=1 "
+            "(or AVJ_FORCE_SIMT=1) to run it on the fp32-FMA check kernel instead.",
+            layout, M, N, K, lda, ldb, (int)(reinterpret_cast<uintptr_t>(A) & 15), (int)(reinterpret_cast<uintptr_t>(B) & 15));
   return avj_gemm_simt(dtype, layout, A, B, C, M, N, K, lda, ldb, ldc, ep, as_stream(stream));
 }
 

@@ -31,8 +31,14 @@ void avj_set_error(const char* fmt, ...);
     }                                                                            \
   } while (0)
 
+// every kernel launch of the library is followed by AVJ_LAUNCH_CHECK(): it also feeds the launch counter that
+// avj_launch_count() reports (bench.py's `gpu_launches` is this counter's difference over the timed region).
+extern unsigned long long g_avj_launches;
+#define AVJ_COUNT_LAUNCH() (void)__atomic_add_fetch(&g_avj_launches, 1ull, __ATOMIC_RELAXED)
+
 #define AVJ_LAUNCH_CHECK()                                                       \
   do {                                                                           \
+    AVJ_COUNT_LAUNCH();                                                          \
     cudaError_t e__ = cudaGetLastError();                                        \
     if (e__ != cudaSuccess) {                                                    \
       avj_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), \

@@ -608,6 +608,75 @@ extern "C" int avj_sumsq(const float* x, int64_t n, float* out, float* ws, void*
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// Per-parameter statistics over a flat buffer in ONE pass (grad_logger / adamw_logger,
+// src/utils/logging.py:91-118): out[s] += sum over segment s of x^2 (mode 0) or |x| (mode 1).
+// seg_off[0..nseg] are ascending element offsets (multiples of 4; the zero padding between
+// parameters belongs to the preceding segment and contributes nothing).  Each block owns a
+// 8192-element chunk: when the chunk lies inside one segment (the common case -- weights are
+// 10^5..10^6 elements) it does a block reduction and one fp64 atomic, otherwise warps that lie
+// inside one segment reduce by shuffle and the few straddling lanes add individually.
+// ------------------------------------------------------------------------------------------
+#define SEG_CHUNK 8192
+__device__ __forceinline__ int seg_of(const int64_t* __restrict__ off, int nseg, int64_t e) {
+  int lo = 0, hi = nseg;                    // largest s with off[s] <= e
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (off[mid] <= e) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void segment_stats_kernel(const float* __restrict__ x, const int64_t* __restrict__ off, int nseg, int mode,
+                                     double* __restrict__ out) {
+  __shared__ float red[32];
+  const int64_t total = off[nseg];
+  const int64_t c0 = (int64_t)blockIdx.x * SEG_CHUNK;
+  const int64_t c1 = min(c0 + (int64_t)SEG_CHUNK, total);
+  if (c0 >= total) return;
+  const int s_first = seg_of(off, nseg, c0), s_last = seg_of(off, nseg, c1 - 1);
+  if (s_first == s_last) {
+    float acc = 0.f;
+    for (int64_t e = c0 + 4 * (int64_t)threadIdx.x; e < c1; e += 4 * (int64_t)blockDim.x) {
+      const float4 a = *reinterpret_cast<const float4*>(x + e);
+      acc += mode == 0 ? (a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w) : (fabsf(a.x) + fabsf(a.y) + fabsf(a.z) + fabsf(a.w));
+    }
+    const float tot = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(out + s_first, (double)tot);
+    return;
+  }
+  for (int64_t e0 = c0; e0 < c1; e0 += 4 * (int64_t)blockDim.x) {
+    const int64_t e = e0 + 4 * (int64_t)threadIdx.x;
+    float acc = 0.f;
+    int sg = -1;
+    if (e < c1) {
+      const float4 a = *reinterpret_cast<const float4*>(x + e);
+      acc = mode == 0 ? (a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w) : (fabsf(a.x) + fabsf(a.y) + fabsf(a.z) + fabsf(a.w));
+      sg = seg_of(off, nseg, e);
+    }
+    const int sg0 = __shfl_sync(0xffffffffu, sg, 0);
+    if (__all_sync(0xffffffffu, sg == sg0)) {
+      const float w = warp_sum(acc);
+      if ((threadIdx.x & 31) == 0 && sg0 >= 0) atomicAdd(out + sg0, (double)w);
+    } else if (sg >= 0) {
+      atomicAdd(out + sg, (double)acc);
+    }
+  }
+}
+
+extern "C" int avj_segment_stats(const float* x, const int64_t* seg_off, int nseg, int64_t total, int mode, double* out,
+                                 void* stream) {
+  AVJ_CHECK(x && seg_off && out, "avj_segment_stats: NULL argument");
+  AVJ_CHECK(mode == 0 || mode == 1, "avj_segment_stats: mode must be 0 (sum of squares) or 1 (sum of |x|)");
+  AVJ_CHECK(total % 4 == 0, "avj_segment_stats: total must be a multiple of 4");
+  if (nseg <= 0 || total == 0) return 0;
+  AvjProfScope prof(AVJ_FAM_OTHER, 4.0 * (double)total, stream, 9, (int)(total >> 20), nseg);
+  const int64_t blocks = (total + SEG_CHUNK - 1) / SEG_CHUNK;
+  segment_stats_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, seg_off, nseg, mode, out);
+  AVJ_LAUNCH_CHECK();
+  return 0;
+}
+
 __global__ void clip_coef_kernel(const float* sumsq, float max_norm, float inv_scale, float* coef) {
   float c = inv_scale;
   if (max_norm > 0.f) {

@@ -23,6 +23,9 @@ def init_distributed(port=37123, rank_and_world_size=(None, None)):
     if rank is None or world is None:
         if 'RANK' in os.environ and 'WORLD_SIZE' in os.environ:
             rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+        elif 'SLURM_NTASKS' in os.environ and 'SLURM_PROCID' in os.environ:        # what the reference reads
+            rank, world = int(os.environ['SLURM_PROCID']), int(os.environ['SLURM_NTASKS'])
+            os.environ.setdefault('MASTER_ADDR', os.environ.get('HOSTNAME', '127.0.0.1'))
         else:
             return 1, 0
     if world <= 1:
@@ -78,6 +81,35 @@ class GradSync(object):
         self._done = {}
         self._left = {}
         self._enc = self._opt = None
+        # measurement (bench.py): CUDA events around the point where the compute stream has to WAIT for the
+        # collectives -- the time between them is the all-reduce time the backward did not hide
+        self.measure = False
+        self._exposed = []
+
+    def _wait_all(self, works):
+        if self.measure and torch.cuda.is_available():
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for w in works:
+                w.wait()
+            b.record()
+            self._exposed.append((a, b))
+        else:
+            for w in works:
+                w.wait()
+
+    def exposed_ms(self, reset=True):
+        """Mean per-step time the compute stream spent blocked on gradient collectives since the last reset
+        (synchronises on the recorded events)."""
+        if not self._exposed:
+            return 0.0
+        vals = []
+        for a, b in self._exposed:
+            b.synchronize()
+            vals.append(a.elapsed_time(b))
+        if reset:
+            self._exposed = []
+        return sum(vals) / len(vals)
 
     # ------------------------------------------------------------------ plain path
     def all_reduce_flat(self, flats, average=True):
@@ -92,8 +124,7 @@ class GradSync(object):
             for lo in range(0, n, self.bucket_elems):
                 chunk = g[lo:min(n, lo + self.bucket_elems)]
                 works.append(tdist.all_reduce(chunk, op=tdist.ReduceOp.SUM, group=self.group, async_op=True))
-        for w in works:
-            w.wait()
+        self._wait_all(works)
         inv = 1.0 / self.world_size
         if not average:
             return inv
@@ -205,8 +236,7 @@ class GradSync(object):
         _ACTIVE = None
         for g in flats:                                       # the complement of what the hooks already started
             self._reduce(g, 0, g.numel())
-        for w in self._works:
-            w.wait()
+        self._wait_all(self._works)
         self._works = []
         for g in flats:                                       # every element exactly once
             iv = sorted(self._done[id(g)])

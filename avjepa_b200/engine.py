@@ -168,12 +168,23 @@ class BlockW(object):
         self.fc2 = LinearW(blk.mlp.fc2, shadows, mode, want_grad)
 
 
+_GRAD_TOUCHES = 0
+
+
+def grad_touch_count():
+    """How many gradient pointers have been handed to backward kernels so far (the fused optimizer compares this
+    with the value it saw when it last cleared its buffers to decide whether zero_grad() has work to do)."""
+    return _GRAD_TOUCHES
+
+
 def grad_ptr(p):
     """fp32 gradient buffer of a parameter, created zero-filled on first use.  Backward kernels
     ACCUMULATE straight into it (weight-gradient GEMMs with a `C +=` epilogue), so no
     per-parameter gradient temporaries exist."""
+    global _GRAD_TOUCHES
     if not p.requires_grad:
         return None
+    _GRAD_TOUCHES += 1
     if p.grad is None:
         p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
     return p.grad.data_ptr()
@@ -299,15 +310,12 @@ class StackRun(object):
             l.pre = sl(i, 'pre') if self.save else None
         return arr
 
-    # kernels per layer issued by avj_stack_forward / avj_stack_backward (for the launch counter)
-    FWD_LAUNCHES_PER_LAYER = 7
-
     def forward(self, blocks, norm, out_ptr, out_dtype):
         """blocks: list[BlockW]; norm: NormW or None.  Writes LN(x_L) to out_ptr."""
         R, D = self.R, self.D
         if self.L > 0:
             desc, arr = self._stack_desc(), self._layer_array(blocks)
-            _cabi.call('avj_stack_forward', C.byref(desc), arr, stream(), launches=self.FWD_LAUNCHES_PER_LAYER * self.L)
+            _cabi.call('avj_stack_forward', C.byref(desc), arr, stream())
         self.x_last = self.x_in(self.L)
         if norm is not None:
             layernorm_fwd(self.x_last, norm.w, norm.b, out_ptr, out_dtype, self.mean_f, self.rstd_f, R, D, norm.eps)
@@ -354,8 +362,5 @@ class StackRun(object):
                 assert len(layer_events) == self.L
                 ev_arr = (C.c_void_p * self.L)(*[int(e.cuda_event) for e in layer_events])
             scs = _cabi.StackScratch(cur, nxt, dx_lp, d_hid, d_qkv, d_h, d_o, ws, ev_arr)
-            w0 = blocks[0]
-            per_layer = 8 + 2 * sum(1 for g in (w0.fc2.gb, w0.fc1.gb, w0.proj.gb, w0.qkv.gb) if g is not None) \
-                + sum(1 for g in (w0.fc2.gw, w0.fc1.gw, w0.proj.gw, w0.qkv.gw) if g is not None) + 3
-            _cabi.call('avj_stack_backward', C.byref(desc), arr, C.byref(scs), stream(), launches=per_layer * self.L)
+            _cabi.call('avj_stack_backward', C.byref(desc), arr, C.byref(scs), stream())
         return cur

@@ -15,6 +15,19 @@ reference's LR/WD schedulers, ``state_dict`` consumers and ``adamw_logger`` keep
   host sync).
 
 Algorithmic HBM bytes per parameter: 16 read + 12 write (+4 grad zero, +8 EMA, +4 shadows).
+
+Differences from ``torch.optim.AdamW`` that a caller can observe (documented, covered by tests):
+
+* the kernel updates EVERY trainable element of a range each step, so a parameter that received no gradient still
+  has weight decay and moment decay applied (torch skips parameters whose ``.grad`` is ``None``).  In the AV-JEPA
+  step every trainable parameter receives a gradient every iteration (both mask-token sets are used, both
+  modalities are embedded), so the two rules coincide on the path this package serves;
+* ``step()`` leaves the gradients in place by default -- the reference loop reads them AFTER the step
+  (``grad_logger``, ``app/avjepa/train.py:526-529``) and then calls ``zero_grad()``.  ``step(zero_grads=True)``
+  (what :class:`~avjepa_b200.app.avjepa.train.TrainStep` uses) zeroes them inside the same kernel pass instead;
+* ``zero_grad()`` keeps the flat views (never sets ``.grad`` to ``None``) and skips the memset only when the last
+  ``step(zero_grads=True)`` already cleared the buffers and no backward has touched them since
+  (:func:`avjepa_b200.engine.grad_ptr` counts every hand-out of a gradient pointer).
 """
 import math
 
@@ -147,15 +160,17 @@ class FusedAdamWEMA(torch.optim.Optimizer):
 
     # ------------------------------------------------------------------ grads
     def zero_grad(self, set_to_none=False):
-        """Gradients live in flat buffers that the step kernel already zeroed; keep the views."""
+        """Zero the flat gradient buffers (the per-parameter ``.grad`` views stay).  A no-op only when the last
+        ``step(zero_grads=True)`` cleared them in-kernel and no backward handed out a gradient pointer since."""
         self.ensure_built()
-        if self._dirty_grads:
-            for r in self._ranges:
-                if r['g'] is not None:
-                    r['g'].zero_()
-            self._dirty_grads = False
+        if self._clean_at == engine.grad_touch_count():
+            return
+        for r in self._ranges:
+            if r['g'] is not None:
+                r['g'].zero_()
+        self._clean_at = engine.grad_touch_count()
 
-    _dirty_grads = True
+    _clean_at = -1          # engine.grad_touch_count() at the moment the buffers were last known to be all-zero
 
     def flat_grads(self):
         self.ensure_built()
@@ -175,10 +190,10 @@ class FusedAdamWEMA(torch.optim.Optimizer):
 
     # ------------------------------------------------------------------ step
     @torch.no_grad()
-    def step(self, closure=None, ema_momentum=None, inv_loss_scale=1.0, coef_by_group=None):
+    def step(self, closure=None, ema_momentum=None, inv_loss_scale=1.0, coef_by_group=None, zero_grads=False):
         """One AdamW step on every group; EMA for paired ranges when `ema_momentum` is given.
         `coef_by_group`: optional {group index -> device float tensor} gradient multipliers
-        (unscale x clip), else `inv_loss_scale` is applied."""
+        (unscale x clip), else `inv_loss_scale` is applied.  `zero_grads`: clear the gradients in the same pass."""
         self.ensure_built()
         self._step += 1
         for r in self._ranges:
@@ -204,7 +219,7 @@ class FusedAdamWEMA(torch.optim.Optimizer):
                 a.eps = float(g['eps'])
                 a.step = self._step
                 a.skip_update = 0
-                a.zero_grad = 1
+                a.zero_grad = 1 if zero_grads else 0
                 if coef_by_group is not None and r['group'] in coef_by_group:
                     a.scale_ptr = coef_by_group[r['group']].data_ptr()
                 elif inv_loss_scale != 1.0:
@@ -214,8 +229,62 @@ class FusedAdamWEMA(torch.optim.Optimizer):
                     a.scale_ptr = None
             _cabi.call('avj_adamw_ema_step', C.byref(a), engine.stream())
         self._step_t += 1
-        self._dirty_grads = False
+        self._clean_at = engine.grad_touch_count() if zero_grads else -1
         return None
+
+    def scale_grads(self, factor):
+        """Multiply every flat gradient buffer by `factor` (GradScaler.unscale_ semantics for a scale != 1)."""
+        self.ensure_built()
+        for r in self._ranges:
+            if r['g'] is not None:
+                r['g'].mul_(float(factor))
+
+    # ------------------------------------------------------------------ per-parameter statistics (logging)
+    def _segments(self, r):
+        """Device int64 offsets [n_params + 1] of range r (cached)."""
+        seg = r.get('seg')
+        if seg is None:
+            offs = list(r['offs']) + [r['flat'].numel()]
+            seg = torch.tensor(offs, dtype=torch.int64, device=r['flat'].device)
+            r['seg'] = seg
+        return seg
+
+    def segment_stats(self, which, group_filter=None):
+        """One pass per flat buffer: fp64 device vector with one entry per parameter of the selected ranges --
+        sum of squares of the gradient (`which='g'`) or sum of |.| of a moment buffer (`'m'`, `'v'`).
+        Returns (names-aligned parameter list, device tensor).  No host synchronisation."""
+        self.ensure_built()
+        mode = 0 if which == 'g' else 1
+        ps, outs = [], []
+        for r in self._ranges:
+            buf = r.get(which)
+            if buf is None or (group_filter is not None and not group_filter(r)):
+                continue
+            out = torch.zeros(len(r['params']), dtype=torch.float64, device=buf.device)
+            _cabi.call('avj_segment_stats', buf.data_ptr(), self._segments(r).data_ptr(), len(r['params']), buf.numel(), mode,
+                       out.data_ptr(), engine.stream())
+            ps += r['params']
+            outs.append(out)
+        if not outs:
+            return [], None
+        return ps, torch.cat(outs)
+
+    def state_dict(self):
+        """torch.optim-compatible state: every parameter gets its OWN `step` tensor and contiguous clones of its
+        moments (not views into the flat buffers, not one shared counter), so the dict loads into a stock
+        ``torch.optim.AdamW`` -- the reference's optimizer -- and steps correctly there."""
+        sd = super().state_dict()
+        state = {}
+        for k, st in sd['state'].items():             # the packed dicts alias self.state[p]: build fresh ones
+            st = dict(st)
+            if 'step' in st:
+                st['step'] = torch.tensor(float(self._step))
+            for name in ('exp_avg', 'exp_avg_sq'):
+                if torch.is_tensor(st.get(name)):
+                    st[name] = st[name].detach().clone().contiguous()
+            state[k] = st
+        sd['state'] = state
+        return sd
 
     def load_state_dict(self, state_dict):
         """Accepts a torch.optim.AdamW state dict (reference checkpoints, app/avjepa/utils.py:63);
@@ -227,4 +296,5 @@ class FusedAdamWEMA(torch.optim.Optimizer):
         self._flat = None
 
     def mark_grads_dirty(self):
-        self._dirty_grads = True
+        """Kept for callers of the round-1 API: forces the next zero_grad() to clear the buffers."""
+        self._clean_at = -1

@@ -1,20 +1,27 @@
 """Benchmark of the AV-JEPA pre-training step (BASELINE.json metric: clips/sec/GPU, ViT-L/16).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+    python bench.py --impl reference --gpus N --steps K ...  # the UNMODIFIED reference (baseline/_ref) on host cores
+    python bench.py --model vit_base --batch 32              # BASELINE config 2;  --model vit_huge: config 4
+    python bench.py --frozen-forward --batch 64              # BASELINE config 5: no-grad encoder forward, N = 1664
 
-A "step" is one full iteration of the hot path (schedules, target fwd, 2x context fwd/bwd, 2x
-predictor fwd/bwd, L1 latent loss, [grad all-reduce], AdamW, EMA) on one batch of synthetic
-clips shaped like configs/pretrain/vitl16.yaml: B=24 per GPU, 16x224x224 video + 128x192 log-mel,
-multiblock masks from the collator under torch.manual_seed(234), random-init weights.
+A "step" is one full iteration of the hot path (schedules, target fwd, 2x context fwd/bwd, 2x predictor fwd/bwd, L1
+latent loss, [grad all-reduce], AdamW, EMA) on one batch of synthetic clips shaped like configs/pretrain/vitl16.yaml:
+B=24 per GPU, 16x224x224 video + 128x192 log-mel, multiblock masks from the collator under torch.manual_seed(234),
+random-init weights.
 
 Printed JSON (one line, rank 0):
-  value        whole-job clips/s with inputs resident in HBM (CUDA events, max over ranks)
-  e2e          same through the public API with HOST inputs: per step a pinned-host -> device copy
-               of clips, spectrogram and masks and a device -> host read of the loss
-  roofline     dominant kernel (tcgen05 GEMM): FLOPs / CUDA-event time of every GEMM launch of one
-               instrumented step, against the measured bf16 peak in MEASURED_PEAKS.json
-  cpu_baseline the CPU oracle (port of the reference step) timed on this host on a bounded sample
+  value          whole-job clips/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e            same through the public API with HOST inputs: per step a pinned-host -> device copy of clips,
+                 spectrogram and masks and a device -> host read of the loss
+  roofline       the launch class (kernel x shape) with the largest total time in one instrumented step -- across ALL
+                 kernel families -- against the measured peaks in MEASURED_PEAKS.json; plus all_gemm / attention / step
+  parity         the first thing the run does (N = 1): forward + backward of the SAME model at B = 2 against the fp32
+                 CPU oracle (loss, global gradient error, and the oracle's own bf16-autocast error beside it)
+  reference_gpu  the unmodified reference (stock PyTorch eager, bf16 autocast, cuBLAS + SDPA) on the same GPU, same
+                 batch / masks / inputs, with and without its grad_logger / adamw_logger syncs -- the real competitor
+  cpu_baseline   the reference's own CPU path (baseline/_ref; the oracle port if that is absent) on a bounded sample
+  comm_exposed_ms  (N > 1) time per step the compute stream waited for gradient collectives
 """
 import argparse
 import json
@@ -134,41 +141,61 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline / reference arm: the oracle port of the reference step on host cores
+# CPU baseline / reference arm: the reference's own implementation of the step on host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_oracle_rate(model, sample_batch, steps, warmup, budget_s=200.0):
+def model_cfg(model, batch, fp32=False):
+    cfg = json.loads(json.dumps(YAML_LIKE))
+    cfg['model']['model_name'] = model
+    cfg['data']['batch_size'] = batch
+    if fp32:
+        cfg['meta']['dtype'] = 'float32'
+    return cfg
+
+
+def cpu_reference_rate(model, sample_batch, steps, warmup, budget_s=None):
+    """The reference step on this host's cores: the live, unmodified reference modules (baseline/_ref, kind
+    "reference") when installed, else the oracle port (kind "port").  fp32 -- CUDA autocast / GradScaler disable
+    themselves without a GPU, exactly as in the reference.  Returns (cpu_baseline dict, median s/step, timed steps)."""
     import torch
-    from oracle import avjepa_oracle as O
-    from avjepa_b200.app.avjepa.utils import init_audio_video_model
     import logging
     logging.disable(logging.CRITICAL)
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    torch.manual_seed(234)
-    enc, pred = init_audio_video_model(device=torch.device('cpu'), model_name=model, pred_depth=PRED_DEPTH,
-                                       pred_embed_dim=PRED_DIM, uniform_power=True, use_mask_tokens=True, num_mask_tokens=2)
-    strip = lambda m: {k[len('backbone.'):]: v.detach().float() for k, v in m.state_dict().items()}  # noqa: E731
-    st = O.StepState(strip(enc), strip(pred), heads=MODEL_DIMS[model][2])
-    del enc, pred
     ev, ea, pv, pa = sample_masks(1, sample_batch)[0]
-    clips, asgram = O.synthetic_batch(sample_batch, 0)
-    times = []
-    t_begin = time.time()
-    done = 0
+    g = torch.Generator().manual_seed(1000)
+    clips = torch.randn(sample_batch, 3, 16, 224, 224, generator=g)
+    asgram = -80.0 * torch.rand(sample_batch, 1, 128, 192, generator=g)
+    from baseline import reference_step as R
+    if R.available():
+        kind = 'reference'
+        tr = R.ReferenceTrainer(model_cfg(model, sample_batch), 'cpu', with_loggers=True)
+        run = lambda: tr.train_step(clips, asgram, ev, ea, pv, pa)  # noqa: E731
+        what = 'the unmodified reference modules from baseline/_ref (restated train_step, grad/adamw loggers on)'
+    else:
+        kind = 'port'
+        from oracle import avjepa_oracle as O
+        from avjepa_b200.app.avjepa.utils import init_audio_video_model
+        torch.manual_seed(234)
+        enc, pred = init_audio_video_model(device=torch.device('cpu'), model_name=model, pred_depth=PRED_DEPTH,
+                                           pred_embed_dim=PRED_DIM, uniform_power=True, use_mask_tokens=True, num_mask_tokens=2)
+        strip = lambda m: {k[len('backbone.'):]: v.detach().float() for k, v in m.state_dict().items()}  # noqa: E731
+        st = O.StepState(strip(enc), strip(pred), heads=MODEL_DIMS[model][2])
+        del enc, pred
+        run = lambda: O.train_step(st, clips, asgram, ev, ea, pv, pa)  # noqa: E731
+        what = 'oracle/avjepa_oracle.py (port of the reference step) on torch CPU'
+    times, t_begin = [], time.time()
     for i in range(warmup + steps):
         t0 = time.time()
-        O.train_step(st, clips, asgram, ev, ea, pv, pa)
+        run()
         dt = time.time() - t0
         if i >= warmup:
             times.append(dt)
-            done += 1
-        # keep the whole run bounded: stop early rather than run for many minutes
-        if time.time() - t_begin + dt > budget_s and done >= 1:
-            break
+        if budget_s is not None and len(times) >= 3 and time.time() - t_begin + dt > budget_s:
+            break                      # bounded leg of the default bench run: at least 3 timed steps, then stop
     med = statistics.median(times)
-    return dict(value=sample_batch / med, unit='clips/s', cores=cores, kind='port',
-                sample=f'{model} full step (fwd+bwd+AdamW+EMA) fp32, batch {sample_batch}, {done} timed step(s) after '
-                       f'{min(warmup, i)} warm-up, median {med:.2f} s/step, oracle/avjepa_oracle.py on torch CPU'), med, done
+    return dict(value=sample_batch / med, unit='clips/s', cores=cores, kind=kind, batch=sample_batch,
+                sample=f'{model} full step (fwd+bwd+AdamW+EMA) fp32, batch {sample_batch} (bounded sample of the batch-24 '
+                       f'workload), {len(times)} timed steps after {min(warmup, i)} warm-up, median {med:.2f} s/step, {what}'), med, len(times)
 
 
 def run_reference_arm(args):
@@ -176,54 +203,235 @@ def run_reference_arm(args):
     if rank != 0:
         return
     model = args.model
-    base, med, done = cpu_oracle_rate(model, args.cpu_sample_batch, args.steps, min(args.warmup, 1))
+    base, med, done = cpu_reference_rate(model, args.cpu_sample_batch, args.steps, args.warmup)
     line = dict(metric='clips/sec/GPU, ViT-L/16 AV-JEPA step', value=base['value'], unit='clips/s', n_gpus=args.gpus,
-                steps=done, warmup=min(args.warmup, 1), ms_per_step=med * 1000.0, higher_is_better=True, scaling='weak',
+                steps=done, warmup=args.warmup, ms_per_step=med * 1000.0, higher_is_better=True, scaling='weak',
                 vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
-                config=dict(workload=f'{model} AV-JEPA pretrain step, vitl16.yaml shape, bounded sample batch '
-                                     f'{args.cpu_sample_batch} on host cores'),
+                config=dict(workload=f'{model} AV-JEPA pretrain step (configs/pretrain/vitl16.yaml shape), bounded sample: batch '
+                                     f'{args.cpu_sample_batch} of the batch-{args.batch} workload, on host cores',
+                            batch=args.cpu_sample_batch),
                 cpu_baseline=base,
                 e2e=dict(value=base['value'], unit='clips/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     print(json.dumps(line), flush=True)
 
 
+def reference_gpu_rate(model, batch, dev, host_clips, host_asgram, mask_sets, steps=5, warmup=2):
+    """The real competitor: the unmodified reference, stock PyTorch eager under bf16 autocast
+    (cuBLAS / cuDNN / SDPA), same GPU, same batch, masks and inputs -- with and without its per-parameter logging
+    syncs (src/utils/logging.py:91-118).  Returns a dict or {'unavailable': why}."""
+    import torch
+    from baseline import reference_step as R
+    if not R.available():
+        return dict(unavailable='baseline/_ref not installed (tools/install_reference.sh)')
+    out = dict(batch=batch, steps=steps, warmup=warmup, dtype='bf16 autocast (torch.cuda.amp, GradScaler)',
+               how='baseline/reference_step.py: restated train_step around the live reference modules, CUDA events')
+    clips, asgram = host_clips.to(dev), host_asgram.to(dev)
+    for tag, loggers in (('with_loggers', True), ('no_loggers', False)):
+        try:
+            tr = R.ReferenceTrainer(model_cfg(model, batch), dev, with_loggers=loggers)
+            dm = [[[m.to(dev) for m in grp] for grp in s] for s in mask_sets[:steps + warmup]]
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            last = None
+            for i in range(steps + warmup):
+                if i == warmup:
+                    torch.cuda.synchronize()
+                    e0.record()
+                last = tr.train_step(clips, asgram, *dm[i])
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[tag] = dict(ms_per_step=ms, clips_per_s=batch / (ms * 1e-3), loss=last['loss'])
+        except Exception as e:      # the competitor arm must never take the bench line down with it
+            out[tag] = dict(error=f'{type(e).__name__}: {e}'[:300])
+        finally:
+            tr = None
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def dominant_gemm(csv_path):
-    """The GEMM launch class with the largest total device time in the instrumented step (avj_prof_dump CSV)."""
+FAM = ['gemm', 'attn_fwd', 'attn_bwd', 'ln_fwd', 'ln_bwd', 'colsum', 'optimizer', 'other']
+KERNEL_OF = {0: 'gemm_umma2_kernel / gemm_umma_kernel (tcgen05, TMA)', 1: 'fa_fwd_umma_kernel (tcgen05, TMEM softmax)',
+             2: 'fa_bwd_umma_kernel (tcgen05, two passes)', 3: 'layernorm_fwd_kernel', 4: 'layernorm_bwd_kernel',
+             5: 'colsum kernels', 6: 'adamw_ema_kernel', 7: 'row kernels'}
+
+
+def launch_label(f, d):
+    """Same labels as tools/step_breakdown.py (and the keys of profiles/*ncu_traffic.json)."""
+    if f == 0:
+        bits = d[0]
+        lay = ['NT', 'NN', 'TN'][bits & 3]
+        epi = '+'.join(nm for b, nm in ((4, 'bias'), (8, 'gelu'), (16, 'res'), (32, 'accum'), (64, 'dact'), (128, 'f32out')) if bits & b)
+        return f'gemm {lay} {d[1]}x{d[2]}x{d[3]} {epi}'.strip()
+    if f in (1, 2):
+        return f'{FAM[f]} B{d[0]} N{d[1]} H{d[2]} hd{d[3]}'
+    return f'{FAM[f]} {d[0]}x{d[1]}'
+
+
+def launch_classes(csv_path):
+    """{(family, label): [launches, total ms, total work]} of the instrumented step (avj_prof_dump CSV)."""
     import csv
     groups = {}
     with open(csv_path) as f:
         for r in csv.DictReader(f):
-            if int(r['family']) != 0:
-                continue
-            key = tuple(int(r[f'd{i}']) for i in range(4))
-            g = groups.setdefault(key, [0, 0.0, 0.0])
+            fam = int(r['family'])
+            d = [int(r[f'd{i}']) for i in range(4)]
+            g = groups.setdefault((fam, launch_label(fam, d)), [0, 0.0, 0.0])
             g[0] += 1
             g[1] += float(r['ms'])
             g[2] += float(r['work'])
-    (bits, M, N, K), (n, ms, work) = max(groups.items(), key=lambda kv: kv[1][1])
-    lay = ['NT', 'NN', 'TN'][bits & 3]
-    epi = '+'.join(nm for b, nm in ((4, 'bias'), (8, 'gelu'), (16, 'res'), (32, 'accum'), (64, 'dact'), (128, 'f32out')) if bits & b)
-    return dict(label=f'gemm {lay} {M}x{N}x{K} {epi}'.strip(), n=n, ms=ms, us=ms / n * 1e3, flops=work / n,
-                tflops=work / (ms * 1e-3) / 1e12)
+    return groups
 
 
 def ncu_traffic(label):
-    """dram bytes per launch of `label` from the committed ncu --set full capture (profiles/r1_ncu_traffic.json)."""
-    path = os.path.join(ROOT, 'profiles', 'r1_ncu_traffic.json')
-    try:
-        with open(path) as f:
-            tab = json.load(f)
-    except (OSError, ValueError):
-        return None, 'profiles/r1_ncu_traffic.json not found'
-    e = tab.get(label)
-    if e is None:
-        return None, f'no ncu capture for "{label}"'
-    return e['dram_read_bytes'] + e['dram_write_bytes'], (f"ncu dram read {e['dram_read_bytes']} + write {e['dram_write_bytes']} B per launch; "
-                                                          f"algorithmic {e['algorithmic_bytes']} B; {e['capture']}")
+    """dram bytes per launch of `label` from the committed ncu --set full captures (profiles/*ncu_traffic.json)."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', '*ncu_traffic.json')), reverse=True):
+        try:
+            with open(path) as f:
+                tab = json.load(f)
+        except (OSError, ValueError):
+            continue
+        e = tab.get(label)
+        if e is not None:
+            return e['dram_read_bytes'] + e['dram_write_bytes'], (
+                f"{os.path.basename(path)}: ncu dram read {e['dram_read_bytes']} + write {e['dram_write_bytes']} B per launch; "
+                f"algorithmic {e['algorithmic_bytes']} B; {e['capture']}")
+    return None, f'no ncu --set full capture committed for "{label}"'
+
+
+def build_roofline(dump_path, fam, ms_step, step_tflops, peaks):
+    """roofline block: the DOMINANT launch class of the step (largest total device time, any family), with the whole
+    GEMM family, both attention families and the whole step beside it."""
+    classes = launch_classes(dump_path)
+    (f, label), (n, ms, work) = max(classes.items(), key=lambda kv: kv[1][1])
+    tensor = f in (0, 1, 2)
+    peak = peaks['bf16_sustained'] if tensor else peaks['hbm']
+    rate = work / (ms * 1e-3) / (1e12 if tensor else 1e9)
+    traffic, note = ncu_traffic(label)
+    breakdown = {}
+    for name, (ms_f, w, cnt) in fam.items():
+        if cnt == 0:
+            continue
+        t = name in ('gemm', 'attention_fwd', 'attention_bwd')
+        r = w / (ms_f * 1e-3) / (1e12 if t else 1e9) if ms_f > 0 else 0.0
+        breakdown[name] = dict(ms=round(ms_f, 3), launches=cnt, achieved=round(r, 1), unit='TFLOP/s' if t else 'GB/s',
+                               frac=round(r / (peaks['bf16_sustained'] if t else peaks['hbm']), 3),
+                               share_of_step=round(ms_f / ms_step, 3))
+    top5 = sorted(classes.items(), key=lambda kv: -kv[1][1])[:8]
+    g_ms, g_fl, g_n = fam['gemm']
+    all_gemm = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    return dict(bound='tensor' if tensor else 'hbm', kernel=f'{KERNEL_OF[f]}: {label}', achieved=rate, peak=peak,
+                unit='TFLOP/s' if tensor else 'GB/s', frac=rate / peak, traffic=traffic, traffic_note=note,
+                algorithmic_work_per_launch=work / n, avg_launch_us=ms / n * 1e3, launches=n, share_of_step=ms / ms_step,
+                peak_source=f'{peaks["src"]} {"sustained bf16" if tensor else "HBM copy"} (kernel timed inside a long step)',
+                all_gemm=dict(achieved=all_gemm, frac=all_gemm / peaks['bf16_sustained'], launches=g_n, ms_per_step=g_ms,
+                              share_of_step=g_ms / ms_step),
+                step=dict(achieved=step_tflops, unit='TFLOP/s', frac_of_sustained=step_tflops / peaks['bf16_sustained'],
+                          frac_of_burst=step_tflops / peaks['bf16_burst']),
+                top_classes=[dict(label=k[1], ms=round(v[1], 3), launches=v[0],
+                                  achieved=round(v[2] / (v[1] * 1e-3) / (1e12 if k[0] < 3 else 1e9), 1)) for k, v in top5],
+                families=breakdown)
+
+
+def parity_block(model, dev):
+    """Forward + backward of `model` at B = 2 (golden masks, seeded inputs) on the product path against the fp32 CPU
+    oracle -- the checker, never the thing measured -- with the oracle's own bf16-autocast error beside it."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import step_support as S
+    t0 = time.time()
+    res = S.config_parity(model, MODEL_DIMS[model][2], dev)
+    fam = res.pop('families')
+    res['worst_family'] = max(fam.items(), key=lambda kv: kv[1]['rel'])[0]
+    res['worst_family_rel'] = fam[res['worst_family']]['rel']
+    res['bars'] = 'loss_rel <= 1e-2; grad_rel <= max(1e-2, 1.25 x autocast_grad_rel)'
+    res['ok'] = bool(res['loss_rel'] <= 1e-2 and res['grad_rel'] <= max(1e-2, 1.25 * res.get('autocast_grad_rel', 0.0)))
+    res['seconds'] = round(time.time() - t0, 1)
+    return res
+
+
+def run_frozen_forward(args):
+    """BASELINE config 5: frozen-encoder forward (no masks, all 1664 tokens, no grad) at large batch -- the
+    av_prediction / attentive-probe evaluation's encoder call (app/avprediction/train.py:455-474)."""
+    import torch
+    import torch.distributed as tdist
+    from avjepa_b200 import _cabi
+    from avjepa_b200.app.avjepa.utils import init_audio_video_model
+    from avjepa_b200.dist import init_distributed
+    import logging
+    logging.disable(logging.CRITICAL)
+    world, rank = init_distributed()
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    _cabi.load()
+    torch.manual_seed(234)
+    enc, _ = init_audio_video_model(device=dev, model_name=args.model, pred_depth=1, pred_embed_dim=PRED_DIM, uniform_power=True,
+                                    use_mask_tokens=True, num_mask_tokens=2)
+    for p in enc.parameters():
+        p.requires_grad = False
+    B, K, W = args.batch, args.steps, args.warmup
+    g = torch.Generator().manual_seed(1000 + rank)
+    host_clips = torch.randn(B, 3, 16, 224, 224, generator=g).pin_memory()
+    host_asgram = (-80.0 * torch.rand(B, 1, 128, 192, generator=g)).pin_memory()
+    D, depth, _ = MODEL_DIMS[args.model]
+    flops_clip = depth * (24 * 1664 * D * D + 4 * 1664 * 1664 * D) + 2 * 1568 * 1536 * D + 2 * 96 * 256 * D
+
+    def loop(e2e):
+        c, a = host_clips.to(dev), host_asgram.to(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = 0
+        for i in range(K + W):
+            if i == W:
+                if world > 1:
+                    tdist.barrier()
+                torch.cuda.synchronize()
+                n0 = _cabi.launch_count()
+                e0.record()
+            with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
+                if e2e:
+                    c, a = host_clips.to(dev, non_blocking=True), host_asgram.to(dev, non_blocking=True)
+                out = enc(c, a)
+                if e2e:
+                    chk = float(out[:, 0, 0].sum())             # D2H of a per-clip feature every step
+        e1.record()
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / K, _cabi.launch_count() - n0
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, launches = loop(False)
+    clocks = sampler.stop()
+    ms_e2e, _ = loop(True)
+    t = torch.tensor([ms, ms_e2e], device=dev)
+    if world > 1:
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        tdist.barrier()
+        tdist.destroy_process_group()
+    if rank != 0:
+        return
+    ms, ms_e2e = float(t[0]), float(t[1])
+    peaks = read_peaks()
+    tf = flops_clip * B / (ms * 1e-3) / 1e12
+    line = dict(metric='clips/sec/GPU, ViT-L/16 frozen-encoder forward', value=world * B / (ms * 1e-3), unit='clips/s', n_gpus=world,
+                steps=K, warmup=W, ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16',
+                data='synthetic',
+                config=dict(workload=f'{args.model} frozen-encoder forward (BASELINE config 5), no masks, 1664 tokens, batch {B}/GPU',
+                            parallelism=f'dp{world} (replicas, no collective)', l2='activations (>2 GB/step) exceed the 126 MB L2',
+                            step_tflops_per_gpu=tf, frac_of_bf16_peak=tf / peaks['bf16_sustained'], flops_per_clip=flops_clip),
+                e2e=dict(value=world * B / (ms_e2e * 1e-3), unit='clips/s', h2d_bytes_per_step=int(host_clips.numel() * 4 + host_asgram.numel() * 4),
+                         d2h_bytes_per_step=4, ms_per_step=ms_e2e),
+                gpu_launches=int(launches), clocks=clocks,
+                roofline=dict(bound='tensor', kernel='whole forward (GEMM + attention)', achieved=tf, peak=peaks['bf16_sustained'],
+                              unit='TFLOP/s', frac=tf / peaks['bf16_sustained'], traffic=None), cpu_baseline=None)
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -236,6 +444,10 @@ def main():
     ap.add_argument('--batch', type=int, default=24, help='clips per GPU (vitl16.yaml: 24)')
     ap.add_argument('--cpu-sample-batch', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-parity', action='store_true', help='skip the B=2 oracle parity block')
+    ap.add_argument('--no-reference-gpu', action='store_true', help='skip the reference-on-GPU competitor leg')
+    ap.add_argument('--same-masks', action='store_true', help='N>1: every rank draws the SAME mask lengths (A/B of straggler skew)')
+    ap.add_argument('--frozen-forward', action='store_true', help='BASELINE config 5: no-grad encoder forward at N=1664')
     ap.add_argument('--fp32', action='store_true', help='fp32 check mode instead of bf16')
     ap.add_argument('--profile-only', action='store_true',
                     help='run warm-up + timed steps of the resident loop and exit (driver for ncu launch lists; prints no bench line)')
@@ -246,10 +458,13 @@ def main():
     if args.impl == 'reference':
         run_reference_arm(args)
         return
+    if args.frozen_forward:
+        run_frozen_forward(args)
+        return
 
     import torch
     import torch.distributed as tdist
-    from avjepa_b200 import _cabi, engine
+    from avjepa_b200 import _cabi
     from avjepa_b200.app.avjepa.train import build_training
     from avjepa_b200.dist import init_distributed
     import logging
@@ -261,12 +476,18 @@ def main():
     dev = torch.device('cuda', local)
     _cabi.load()
 
-    cfg = json.loads(json.dumps(YAML_LIKE))
-    cfg['model']['model_name'] = args.model
-    cfg['data']['batch_size'] = args.batch
-    if args.fp32:
-        cfg['meta']['dtype'] = 'float32'
-    step, _, _ = build_training(cfg, dev, world, rank)
+    # ---- parity first: the same model family at B = 2 against the CPU oracle (rank 0 of an N = 1 run only)
+    parity = None
+    if world == 1 and not args.no_parity and not args.fp32 and not args.profile_only:
+        try:
+            parity = parity_block(args.model, dev)
+        except Exception as e:
+            parity = dict(ok=False, error=f'{type(e).__name__}: {e}'[:300])
+        torch.cuda.empty_cache()
+
+    step, _, _ = build_training(model_cfg(args.model, args.batch, args.fp32), dev, world, rank)
+    if step.grad_sync is not None:
+        step.grad_sync.measure = True
     B, K, W = args.batch, args.steps, args.warmup
 
     # ---- synthetic inputs: every rank draws its own clips; masks per step from the collator
@@ -274,7 +495,7 @@ def main():
     host_clips = torch.randn(B, 3, 16, 224, 224, generator=g).pin_memory()
     host_asgram = (-80.0 * torch.rand(B, 1, 128, 192, generator=g)).pin_memory()
     n_sets = 2 * (K + W) + 1
-    mask_sets = sample_masks(n_sets, B, seed=234 + rank)
+    mask_sets = sample_masks(n_sets, B, seed=234 + (0 if args.same_masks else rank))
     host_masks = [tuple([m.pin_memory() for m in grp] for grp in s) for s in mask_sets]
     lens = [[(s[0][i].shape[1], s[1][i].shape[1], s[2][i].shape[1], s[3][i].shape[1]) for i in range(2)] for s in mask_sets]
 
@@ -287,7 +508,7 @@ def main():
         torch.cuda.synchronize()
 
     def timed_loop(first_set, e2e):
-        """Returns (ms per step, flops per clip averaged over the timed steps, launches)."""
+        """Returns (ms per step, flops per clip averaged over the timed steps, launches, last loss, exposed comm ms)."""
         clips_d, asgram_d = host_clips.to(dev), host_asgram.to(dev)
         dev_masks = [to_device(host_masks[first_set + i]) for i in range(K + W)] if not e2e else None
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -301,7 +522,9 @@ def main():
         for i in range(K + W):
             if i == W:
                 barrier()
-                launches = _cabi.launch_count
+                launches = _cabi.launch_count()
+                if step.grad_sync is not None:
+                    step.grad_sync.exposed_ms()
                 ev0.record()
             if e2e:
                 c, a, m = next(feed)
@@ -311,34 +534,35 @@ def main():
         ev1.record()
         barrier()
         ms = ev0.elapsed_time(ev1) / K
-        launches = _cabi.launch_count - launches
+        launches = (_cabi.launch_count() - launches) / K
+        exposed = step.grad_sync.exposed_ms() if step.grad_sync is not None else 0.0
         fl = sum(step_flops(args.model, lens[first_set + i]) for i in range(W, K + W)) / K
         last_loss = float(out[0])
-        return ms, fl, launches, last_loss
+        return ms, fl, launches, last_loss, exposed
 
     sampler = ClockSampler(local)
     sampler.start()
-    ms_res, flops_clip, launches, loss_res = timed_loop(0, e2e=False)
+    ms_res, flops_clip, launches, loss_res, exposed_res = timed_loop(0, e2e=False)
     clocks = sampler.stop()
     if args.profile_only:
         if rank == 0:
-            print(json.dumps(dict(profile_only=True, ms_per_step=ms_res, gpu_launches=int(launches))), flush=True)
+            print(json.dumps(dict(profile_only=True, ms_per_step=ms_res, gpu_launches_per_step=launches)), flush=True)
         return
-    ms_e2e, _, _, loss_e2e = timed_loop(K + W, e2e=True)
+    ms_e2e, _, _, loss_e2e, exposed_e2e = timed_loop(K + W, e2e=True)
 
     # ---- max over ranks
-    t = torch.tensor([ms_res, ms_e2e], device=dev)
+    t = torch.tensor([ms_res, ms_e2e, exposed_res, exposed_e2e], device=dev)
     if world > 1:
         tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
-    ms_res, ms_e2e = float(t[0]), float(t[1])
+    ms_res, ms_e2e, exposed_res, exposed_e2e = (float(x) for x in t)
 
-    # ---- roofline of the dominant kernel: every GEMM launch of one instrumented step
+    # ---- roofline: every GEMM / attention / LayerNorm / column-sum / optimizer launch of ONE extra step is bracketed
+    # with CUDA events on the launch stream inside the library (avj_prof_*); nothing is serialised, so the sum per
+    # class is that class's device time inside a normal step.  The step is COLLECTIVE (it contains the gradient
+    # all-reduce), so every rank runs it; only rank 0 instruments and reports.
     peaks = read_peaks()
     roof = None
-    # the library brackets every GEMM / attention / LayerNorm / column-sum / optimizer launch of ONE extra
-    # step with CUDA events on the launch stream (avj_prof_*); nothing is serialised, so the sum per
-    # family is that family's device time inside a normal step.  The step is COLLECTIVE (it contains the
-    # gradient all-reduce), so every rank runs it; only rank 0 instruments and reports.
+    step_tflops = flops_clip * B / (ms_res * 1e-3) / 1e12
     if rank == 0:
         _cabi.prof_enable(True)
     step(host_clips.to(dev), host_asgram.to(dev), *to_device(host_masks[-1]), epoch=0, sync=True)
@@ -348,28 +572,7 @@ def main():
         dump_path = args.prof_dump or os.path.join(tempfile.gettempdir(), f'avj_prof_{os.getpid()}.csv')
         _cabi.prof_dump(dump_path)
         _cabi.prof_enable(False)
-        g_ms, g_fl, g_n = fam['gemm']
-        peak = peaks['bf16_sustained']
-        breakdown = {}
-        for name, (ms_f, work, n) in fam.items():
-            if n == 0:
-                continue
-            unit = 'TFLOP/s' if name in ('gemm', 'attention_fwd', 'attention_bwd') else 'GB/s'
-            rate = work / (ms_f * 1e-3) / (1e12 if unit == 'TFLOP/s' else 1e9) if ms_f > 0 else 0.0
-            breakdown[name] = dict(ms=round(ms_f, 3), launches=n, achieved=round(rate, 1), unit=unit)
-        # dominant kernel = the GEMM launch class (layout, epilogue, M, N, K) with the largest total time in the step
-        top = dominant_gemm(dump_path)
-        all_gemm = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
-        traffic, traffic_note = ncu_traffic(top['label'])
-        roof = dict(bound='tensor', kernel=f"gemm_umma2_kernel (tcgen05 cta_group::2), {top['label']}",
-                    achieved=top['tflops'], peak=peak, unit='TFLOP/s', frac=top['tflops'] / peak,
-                    traffic=traffic, traffic_note=traffic_note,
-                    algorithmic_flops_per_launch=top['flops'], avg_launch_us=top['us'], launches=top['n'],
-                    share_of_step=top['ms'] / ms_res,
-                    peak_source=f'{peaks["src"]} sustained bf16 (kernel timed inside a long step)',
-                    all_gemm=dict(achieved=all_gemm, frac=all_gemm / peak, launches=g_n, ms_per_step=g_ms,
-                                  share_of_step=g_ms / ms_res),
-                    families=breakdown)
+        roof = build_roofline(dump_path, fam, ms_res, step_tflops, peaks)
 
     if world > 1:
         tdist.barrier()
@@ -377,14 +580,24 @@ def main():
     if rank != 0:
         return
 
-    cpu = None
-    if not args.no_cpu_baseline and world == 1:        # the CPU baseline is an N = 1 artefact (rank 0 would stall the job)
-        cpu, _, _ = cpu_oracle_rate(args.model, args.cpu_sample_batch, 1, 1, budget_s=120.0)
+    # ---- the competitor and the CPU baseline (N = 1 only: rank 0 would stall a multi-rank job)
+    ref_gpu = cpu = None
+    if world == 1:
+        del step
+        torch.cuda.empty_cache()
+        if not args.no_reference_gpu and not args.fp32:
+            ref_gpu = reference_gpu_rate(args.model, B, dev, host_clips, host_asgram, mask_sets)
+            ok = ref_gpu.get('no_loggers', {}).get('clips_per_s')
+            if ok:
+                ref_gpu['speedup_vs_no_loggers'] = (B / (ms_e2e * 1e-3)) / ok
+                wl = ref_gpu.get('with_loggers', {}).get('clips_per_s')
+                ref_gpu['speedup_vs_with_loggers'] = (B / (ms_e2e * 1e-3)) / wl if wl else None
+        if not args.no_cpu_baseline:
+            cpu, _, _ = cpu_reference_rate(args.model, args.cpu_sample_batch, 3, 1, budget_s=150.0)
 
     clips_per_s = world * B / (ms_res * 1e-3)
     e2e_clips = world * B / (ms_e2e * 1e-3)
     h2d = host_clips.numel() * 4 + host_asgram.numel() * 4 + sum(m.numel() * 8 for grp in host_masks[0] for m in grp)
-    step_tflops = flops_clip * B / (ms_res * 1e-3) / 1e12
     line = dict(
         metric='clips/sec/GPU, ViT-L/16 AV-JEPA step', value=clips_per_s, unit='clips/s', n_gpus=world, steps=K, warmup=W,
         ms_per_step=ms_res, higher_is_better=True, scaling='weak', vs_baseline=None,
@@ -392,12 +605,17 @@ def main():
         config=dict(workload=f'{args.model} AV-JEPA pretrain step (configs/pretrain/vitl16.yaml shape), batch {B}/GPU, '
                              f'16x224x224 video + 128x192 log-mel, 2 multiblock masks, predictor depth {PRED_DEPTH}',
                     parallelism=f'dp{world}', l2='inputs+weights (>1.5 GB/step) exceed the 126 MB L2; no explicit flush',
+                    masks='same lengths on every rank' if args.same_masks else 'per-rank collator draws (lengths differ across ranks)',
                     clips_per_s_per_gpu=clips_per_s / world,
                     step_tflops_per_gpu=step_tflops, frac_of_bf16_peak=step_tflops / peaks['bf16_sustained'],
                     flops_per_clip=flops_clip, loss=loss_res),
         e2e=dict(value=e2e_clips, unit='clips/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=12,
                  ms_per_step=ms_e2e, loss=loss_e2e),
-        gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu)
+        gpu_launches=int(round(launches * K)), gpu_launches_per_step=launches, clocks=clocks, roofline=roof, parity=parity,
+        reference_gpu=ref_gpu, cpu_baseline=cpu)
+    if world > 1:
+        line['comm_exposed_ms'] = dict(resident=exposed_res, e2e=exposed_e2e,
+                                       how='CUDA events around the compute stream\'s wait on the gradient all-reduces, mean per step, max over ranks')
     print(json.dumps(line), flush=True)
 
 

@@ -67,9 +67,15 @@ const char* avj_last_error_string(void);
 /* 1 when the device behind the current context is sm_100 and the tcgen05 path is usable. */
 int avj_device_ok(void);
 
+/* Number of kernels this library has launched in the calling process so far (every launch site counts itself);
+ * bench.py reports the difference over its timed region as `gpu_launches`. */
+int64_t avj_launch_count(void);
+
 /* ---- K6: nn.Linear fprop/dgrad/wgrad (src/models/utils/modules.py:25-36,54-77) and the
  *      patch-embed / predictor-embed GEMMs (patch_embed.py:85-101, audiovisionpredictor.py:
- *      232-243).  dtype selects the operand type of A and B. */
+ *      232-243).  dtype selects the operand type of A and B.  bf16 problems run on the tcgen05 kernel and must
+ *      satisfy N % 64 == 0, lda/ldb % 8 == 0, 16-byte aligned A/B (TN: M % 8 == 0); anything else is an ERROR
+ *      (never a silent fp32-FMA fallback) unless AVJ_GEMM_SIMT_FALLBACK=1 / AVJ_FORCE_SIMT=1 is set. */
 int avj_gemm(int dtype, int layout, const void* A, const void* B, void* C,
              int M, int N, int K, int lda, int ldb, int ldc,
              const avj_epilogue* ep, void* stream);
@@ -181,6 +187,13 @@ int avj_adamw_ema_step(const avj_adamw_args* a, void* stream);
 int64_t avj_sumsq_ws_floats(int64_t n);
 int avj_sumsq(const float* x, int64_t n, float* out, float* ws, void* stream);
 int avj_clip_coef(const float* sumsq, float max_norm, float inv_loss_scale, float* coef, void* stream);
+
+/* ---- per-parameter statistics in one pass over a flat fp32 buffer (grad_logger / adamw_logger,
+ *      src/utils/logging.py:91-118, which issue one blocking float() per parameter): out[s] += sum over
+ *      [seg_off[s], seg_off[s+1]) of x^2 (mode 0) or |x| (mode 1).  seg_off: nseg+1 ascending int64 device
+ *      offsets, multiples of 4, seg_off[nseg] == total.  out: fp64 [nseg], ACCUMULATED (caller zeroes). */
+int avj_segment_stats(const float* x, const int64_t* seg_off, int nseg, int64_t total, int mode, double* out,
+                      void* stream);
 
 /* fp32 -> bf16 (or fp32 copy) over a contiguous range: shadow-weight refresh. */
 int avj_cast(const float* in, void* out, int out_dtype, int64_t n, void* stream);

@@ -12,6 +12,11 @@ Fixtures (all small):
                    seeded synthetic inputs: losses, every parameter-gradient norm, samples of
                    gradients, post-step parameter / target checksums
   posemb.npz       samples of the sincos tables
+  ref_checkpoint_micro.pth.tar   a checkpoint WRITTEN BY THE REFERENCE's code path (nn.DataParallel wrappers ->
+                   `module.backbone.*` keys, torch.optim.AdamW state with two steps taken, GradScaler state) for a
+                   micro model (embed 16, depth 1; 32x32x4 clips) -- the wire-format fixture of
+                   tests/test_checkpoint_host.py
+  tensors_misc.npz repeat_interleave_batch outputs (src/utils/tensors.py:65-71)
 The step is restated around the reference's own modules because the reference keeps it in a
 closure that cannot be imported.
 """
@@ -210,6 +215,54 @@ def golden_posemb():
     np.savez_compressed(os.path.join(OUT, 'posemb.npz'), **d)
 
 
+MICRO = dict(img_size=32, patch_size=16, num_frames=4, tubelet_size=2, embed_dim=16, depth=1, num_heads=2)
+
+
+def golden_checkpoint():
+    """What app/avjepa/train.py:298-300,332-350 writes, for a micro AV model: DataParallel-wrapped MultiMask wrappers,
+    the 4-group AdamW of init_opt after two optimizer steps, the (bf16) GradScaler state."""
+    from functools import partial
+    import torch.nn as nn
+    from src.models.audiovision_transformer import AudioVisionTransformer
+    from src.models.audiovisionpredictor import AudioVisionTransformerPredictor
+    from src.models.utils.multimask import AudioVideoMultiMaskWrapper, PredictorMultiMaskWrapper
+    torch.manual_seed(7)
+    ln = partial(nn.LayerNorm, eps=1e-6)
+    enc = AudioVideoMultiMaskWrapper(AudioVisionTransformer(mlp_ratio=4, qkv_bias=True, norm_layer=ln, uniform_power=True, **MICRO))
+    pred = PredictorMultiMaskWrapper(AudioVisionTransformerPredictor(
+        img_size=32, patch_size=16, num_frames=4, tubelet_size=2, embed_dim=16, predictor_embed_dim=8, depth=1, num_heads=2,
+        mlp_ratio=4, qkv_bias=True, norm_layer=ln, uniform_power=True, use_mask_tokens=True, num_mask_tokens=2))
+    tgt = copy.deepcopy(enc)
+    opt, scaler, sched, wd_sched = init_opt(
+        encoder=enc, predictor=pred, wd=0.04, final_wd=0.4, start_lr=2e-4, ref_lr=6.25e-4, final_lr=1e-6,
+        iterations_per_epoch=3, warmup=1, num_epochs=2, ipe_scale=1.25, mixed_precision=True)
+    enc, pred, tgt = (torch.nn.DataParallel(m) for m in (enc, pred, tgt))
+    g = torch.Generator().manual_seed(5)
+    for _ in range(2):
+        sched.step()
+        wd_sched.step()
+        for p in list(enc.parameters()) + list(pred.parameters()):
+            if p.requires_grad:
+                p.grad = torch.randn(p.shape, generator=g) * 1e-2
+        opt.step()
+        opt.zero_grad()
+    save_dict = {
+        'encoder': enc.state_dict(), 'predictor': pred.state_dict(), 'opt': opt.state_dict(),
+        'scaler': None if scaler is None else scaler.state_dict(), 'target_encoder': tgt.state_dict(),
+        'epoch': 1, 'loss': 0.5, 'batch_size': 2, 'world_size': 1, 'lr': 6.25e-4,
+    }
+    torch.save(save_dict, os.path.join(OUT, 'ref_checkpoint_micro.pth.tar'))
+
+
+def golden_misc():
+    from src.utils.tensors import repeat_interleave_batch
+    x = torch.arange(6 * 3, dtype=torch.float32).reshape(6, 3)
+    d = {'rib_in': x.numpy()}
+    for B, rep in ((2, 1), (2, 2), (3, 2), (1, 3), (6, 2)):
+        d[f'rib_B{B}_r{rep}'] = repeat_interleave_batch(x, B, rep).numpy()
+    np.savez_compressed(os.path.join(OUT, 'tensors_misc.npz'), **d)
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -218,4 +271,6 @@ if __name__ == '__main__':
     golden_init()
     golden_init_video()
     golden_step()
+    golden_checkpoint()
+    golden_misc()
     print('golden fixtures written to', OUT, 'torch', torch.__version__)

@@ -60,9 +60,13 @@ class Layer(C.Structure):
     ]
 
 
+MAX_SEGMENTS = 8
+
+
 class Stack(C.Structure):
     _fields_ = [('dtype', C.c_int32), ('B', C.c_int32), ('N', C.c_int32), ('D', C.c_int32), ('H', C.c_int32),
-                ('hidden', C.c_int32), ('L', C.c_int32)]
+                ('hidden', C.c_int32), ('L', C.c_int32), ('n_seg', C.c_int32),
+                ('seg_B', C.c_int32 * MAX_SEGMENTS), ('seg_N', C.c_int32 * MAX_SEGMENTS)]
 
 
 class StackScratch(C.Structure):

@@ -110,7 +110,11 @@ class TrainStep(object):
         (LossScaler is the identity); the scaler object only mirrors the reference call sites."""
         opt = self.optimizer
         if self.grad_sync is not None and hasattr(self.grad_sync, 'begin_step'):
-            self.grad_sync.begin_step(opt, _backbone(self.encoder), n_masks, n_masks)
+            # how many backward calls of each backbone this step makes: ONE when the MultiMask wrappers run all
+            # masks through a single variable-length schedule (the default), else one per mask
+            from avjepa_b200.backbone import merge_masks_enabled
+            n_calls = 1 if merge_masks_enabled() else n_masks
+            self.grad_sync.begin_step(opt, _backbone(self.encoder), n_calls, n_calls)
         loss.backward()
         if self.grad_sync is None:
             return 1.0

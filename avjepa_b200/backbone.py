@@ -76,8 +76,10 @@ def _pos_table(mod, x, name):
     return _f32c(pos)
 
 
-def encoder_forward(mod, x, y, mv, ma, save, mode):
-    """Returns (out [B, N, D] fp32, state).  `y`/`ma` are None for the video-only encoder."""
+def encoder_forward(mod, x, y, masks, save, mode):
+    """`masks`: list of (video_idx, audio_idx) pairs, one per mask (entries None = keep every token); `y` and the
+    audio indices are None for the video-only encoder.  ALL masks run through one variable-length stack
+    (engine.StackRun): sequence group g holds the B sequences of mask g.  Returns ([out_g [B, N_g, D] fp32], state)."""
     engine.require_cuda(x, 'encoder input')
     dev = x.device
     x = _f32c(x)
@@ -90,45 +92,58 @@ def encoder_forward(mod, x, y, mv, ma, save, mode):
     B, Cin, T, H, W = x5.shape
     p, D = mod.patch_size, mod.embed_dim
     n_full_v = (T // tub) * (H // p) * (W // p)
-    mv, ma = _idx(mv, dev), _idx(ma, dev)
-    Kv = mv.shape[1] if mv is not None else n_full_v
-    Ka, n_full_a = 0, 0
+    n_full_a = 0
     if y is not None:
         y = _f32c(y)
         n_full_a = (y.shape[2] // p) * (y.shape[3] // p)
-        Ka = ma.shape[1] if ma is not None else n_full_a
-    N = Kv + Ka
+    groups = []
+    for mv, ma in masks:
+        mv, ma = _idx(mv, dev), _idx(ma, dev)
+        Kv = mv.shape[1] if mv is not None else n_full_v
+        Ka = 0
+        if y is not None:
+            Ka = ma.shape[1] if ma is not None else n_full_a
+        groups.append((mv, ma, Kv, Ka))
     cd = mode.code
-    run = StackRun(B, N, D, mod.num_heads, len(mod.blocks), mode, save, dev)
+    run = StackRun([(B, Kv + Ka) for _, _, Kv, Ka in groups], D, mod.num_heads, len(mod.blocks), mode, save, dev)
     st = _EncState()
-    st.run, st.B, st.N, st.Kv, st.Ka, st.mode = run, B, N, Kv, Ka, mode
+    st.run, st.B, st.mode, st.groups = run, B, mode, groups
+    st.N = groups[0][2] + groups[0][3]
 
     pos_name = 'video_pos_embed' if hasattr(mod, 'video_pos_embed') else 'pos_embed'
     pos_v = _pos_table(mod, x, pos_name)
+    pos_a = _f32c(mod.audio_pos_embed) if y is not None else None
     kd_v = Cin * tub * p * p
-    st.patches_v = torch.empty((B * Kv, kd_v), dtype=mode.torch_dtype, device=dev)
-    _cabi.call('avj_patchify', x5.data_ptr(), _ptr(mv), st.patches_v.data_ptr(), cd, B, Cin, T, H, W, tub, p, Kv, stream())
     pe = mod.patch_embed
-    engine.gemm(mode, GEMM_NT, st.patches_v.data_ptr(), _wptr(pe.proj.weight, mod, mode), run.x_in(0),
-                B * Kv, D, kd_v, kd_v, kd_v, D, F32, bias=_ptr(pe.proj.bias), pos=pos_v.data_ptr(),
-                pos_idx=_ptr(mv), pos_rows=pos_v.shape[1], out_map=rowmap(Kv, N, 0))
-    st.patches_a = None
-    if y is not None and Ka > 0:
-        pos_a = _f32c(mod.audio_pos_embed)
-        kd_a = y.shape[1] * p * p
-        st.patches_a = torch.empty((B * Ka, kd_a), dtype=mode.torch_dtype, device=dev)
-        _cabi.call('avj_patchify', y.data_ptr(), _ptr(ma), st.patches_a.data_ptr(), cd, B, y.shape[1], 1, y.shape[2],
-                   y.shape[3], 1, p, Ka, stream())
-        engine.gemm(mode, GEMM_NT, st.patches_a.data_ptr(), _wptr(pe.audio_proj.weight, mod, mode), run.x_in(0),
-                    B * Ka, D, kd_a, kd_a, kd_a, D, F32, bias=_ptr(pe.audio_proj.bias), pos=pos_a.data_ptr(),
-                    pos_idx=_ptr(ma), pos_rows=pos_a.shape[1], out_map=rowmap(Ka, N, Kv))
-    st.keep = (x5, y, mv, ma, pos_v)       # keep inputs alive until the kernels reading them retire
+    st.patches = []
+    for g, (mv, ma, Kv, Ka) in enumerate(groups):
+        N = Kv + Ka
+        x0 = run.x0_rows(g)
+        pv = torch.empty((B * Kv, kd_v), dtype=mode.torch_dtype, device=dev)
+        _cabi.call('avj_patchify', x5.data_ptr(), _ptr(mv), pv.data_ptr(), cd, B, Cin, T, H, W, tub, p, Kv, stream())
+        engine.gemm(mode, GEMM_NT, pv.data_ptr(), _wptr(pe.proj.weight, mod, mode), x0,
+                    B * Kv, D, kd_v, kd_v, kd_v, D, F32, bias=_ptr(pe.proj.bias), pos=pos_v.data_ptr(),
+                    pos_idx=_ptr(mv), pos_rows=pos_v.shape[1], out_map=rowmap(Kv, N, 0))
+        pa = None
+        if y is not None and Ka > 0:
+            kd_a = y.shape[1] * p * p
+            pa = torch.empty((B * Ka, kd_a), dtype=mode.torch_dtype, device=dev)
+            _cabi.call('avj_patchify', y.data_ptr(), _ptr(ma), pa.data_ptr(), cd, B, y.shape[1], 1, y.shape[2],
+                       y.shape[3], 1, p, Ka, stream())
+            engine.gemm(mode, GEMM_NT, pa.data_ptr(), _wptr(pe.audio_proj.weight, mod, mode), x0,
+                        B * Ka, D, kd_a, kd_a, kd_a, D, F32, bias=_ptr(pe.audio_proj.bias), pos=pos_a.data_ptr(),
+                        pos_idx=_ptr(ma), pos_rows=pos_a.shape[1], out_map=rowmap(Ka, N, Kv))
+        st.patches.append((pv, pa) if save else (None, None))
+    st.keep = (x5, y, [g_[:2] for g_ in groups], pos_v, pos_a)       # keep inputs alive until the kernels reading them retire
     sh = _shadows(mod)
     blocks = [BlockW(b, sh, mode, False) for b in mod.blocks]
 
     if mod.out_layers is not None:
         if save:
             raise NotImplementedError('out_layers is a frozen-eval feature; call under torch.no_grad()')
+        if len(groups) != 1:
+            raise NotImplementedError('out_layers with several masks in one call')
+        N = st.N
         outs = []
         norm = NormW(mod.norm, False)
         for i in range(len(blocks)):
@@ -138,24 +153,25 @@ def encoder_forward(mod, x, y, mv, ma, save, mode):
                 engine.layernorm_fwd(run.x_in(i + 1), norm.w, norm.b, o.data_ptr(), F32, None, None, B * N, D, norm.eps)
                 outs.append(o)
         st.run_keepalive = run
+        st.out_layers = True
         return outs, st
 
-    out = torch.empty((B, N, D), dtype=torch.float32, device=dev)
+    outs = [torch.empty((B, Kv + Ka, D), dtype=torch.float32, device=dev) for _, _, Kv, Ka in groups]
     norm = NormW(mod.norm, False) if mod.norm is not None else None
-    run.forward(blocks, norm, out.data_ptr(), F32)
-    if not save:
-        st.patches_v = st.patches_a = None
-    return out, st
+    run.forward(blocks, norm, [o.data_ptr() for o in outs], F32)
+    return outs, st
 
 
-def encoder_backward(mod, st, dout):
-    run, mode = st.run, st.mode
-    B, N, Kv, Ka, D = st.B, st.N, st.Kv, st.Ka, run.D
+def encoder_backward(mod, st, douts):
+    """douts: one gradient per sequence group (None -> zero)."""
+    run, mode, B, D = st.run, st.mode, st.B, st.run.D
     cd, s = mode.code, mode.size
-    dev = dout.device
-    dout = _f32c(dout)
+    dev = next(d for d in douts if d is not None).device
+    douts = [_f32c(d) if d is not None else torch.zeros((B, Kv + Ka, D), dtype=torch.float32, device=dev)
+             for d, (_, _, Kv, Ka) in zip(douts, st.groups)]
     lib = _cabi.load()
-    extra = engine._align(B * max(Kv, Ka, 1) * D * s) * 2 + 4 * lib.avj_colsum_ws_floats(B * max(Kv, Ka, 1), D) + (1 << 16)
+    kmax = max(max(Kv, Ka, 1) for _, _, Kv, Ka in st.groups)
+    extra = engine._align(B * kmax * D * s) * 2 + 4 * lib.avj_colsum_ws_floats(B * kmax, D) + (1 << 16)
     sc = engine.SCRATCH.get(run.scratch_bytes() + extra, dev)
     sh = _shadows(mod)
     blocks = [BlockW(b, sh, mode, True) for b in mod.blocks]
@@ -163,57 +179,72 @@ def encoder_backward(mod, st, dout):
     from avjepa_b200 import dist as avj_dist
     sync = avj_dist.active_sync()
     evs = sync.layer_events_for(mod, run.L) if sync is not None else None
-    dx0 = run.backward(blocks, norm, dout.data_ptr(), F32, sc, layer_events=evs)
+    dx0 = run.backward(blocks, norm, [d.data_ptr() for d in douts], F32, sc, layer_events=evs)
     if evs is not None:
         sync.on_layers_enqueued(mod, evs)
     pe = mod.patch_embed
-    ws = sc.alloc(4 * lib.avj_colsum_ws_floats(B * max(Kv, Ka, 1), D))
-    dxc = sc.alloc(B * max(Kv, Ka, 1) * D * s)
-    for (K, off, patches, conv) in ((Kv, 0, st.patches_v, pe.proj),
-                                    (Ka, Kv, st.patches_a, getattr(pe, 'audio_proj', None))):
-        if K == 0 or patches is None or conv is None:
-            continue
-        gw, gb = engine.grad_ptr(conv.weight), engine.grad_ptr(conv.bias) if conv.bias is not None else None
-        kd = patches.shape[1]
-        rm = rowmap(K, N, off)
-        if gb is not None:
-            engine.colsum(dx0, F32, D, rm, gb, B * K, D, ws)
-        if gw is not None:
-            engine.copy_rows(dx0, F32, D, rm, dxc, cd, D, IDENTITY, B * K, D)
-            engine.gemm(mode, GEMM_TN, dxc, patches.data_ptr(), gw, D, kd, B * K, D, kd, kd, F32, accumulate=1)
+    ws = sc.alloc(4 * lib.avj_colsum_ws_floats(B * kmax, D))
+    dxc = sc.alloc(B * kmax * D * s)
+    for g, (mv, ma, Kv, Ka) in enumerate(st.groups):
+        N = Kv + Ka
+        dx0_g = dx0 + run.row0[g] * D * 4
+        for (K, off, patches, conv) in ((Kv, 0, st.patches[g][0], pe.proj), (Ka, Kv, st.patches[g][1], getattr(pe, 'audio_proj', None))):
+            if K == 0 or patches is None or conv is None:
+                continue
+            gw, gb = engine.grad_ptr(conv.weight), engine.grad_ptr(conv.bias) if conv.bias is not None else None
+            kd = patches.shape[1]
+            rm = rowmap(K, N, off)
+            if gb is not None:
+                engine.colsum(dx0_g, F32, D, rm, gb, B * K, D, ws)
+            if gw is not None:
+                engine.copy_rows(dx0_g, F32, D, rm, dxc, cd, D, IDENTITY, B * K, D)
+                engine.gemm(mode, GEMM_TN, dxc, patches.data_ptr(), gw, D, kd, B * K, D, kd, kd, F32, accumulate=1)
     if sync is not None:
         sync.on_backward_done('encoder', mod)
 
 
 class EncoderFn(torch.autograd.Function):
-    """autograd node for one encoder call.  Inputs after `ma` are the module's parameters: they
-    are listed so autograd knows the output depends on them; their gradients are accumulated
-    in place by the backward kernels and `None` is returned for them."""
+    """autograd node for one encoder call over n_masks masks.  Inputs after the masks are the module's parameters:
+    they are listed so autograd knows the outputs depend on them; their gradients are accumulated in place by the
+    backward kernels and `None` is returned for them."""
 
     @staticmethod
-    def forward(ctx, mod, save, mode, x, y, mv, ma, *params):
-        out, st = encoder_forward(mod, x, y, mv, ma, save, mode)
-        ctx.mod, ctx.st, ctx.n_params = mod, st, len(params)
-        if isinstance(out, list):
-            return tuple(out)
-        return out
+    def forward(ctx, mod, save, mode, x, y, n_masks, *rest):
+        masks = [(rest[2 * i], rest[2 * i + 1]) for i in range(n_masks)]
+        outs, st = encoder_forward(mod, x, y, masks, save, mode)
+        ctx.mod, ctx.st, ctx.n_rest = mod, st, len(rest)
+        return tuple(outs)
 
     @staticmethod
     def backward(ctx, *douts):
-        dout = douts[0]
-        if dout is not None:
-            encoder_backward(ctx.mod, ctx.st, dout)
+        if any(d is not None for d in douts):
+            if getattr(ctx.st, 'out_layers', False):
+                raise NotImplementedError('out_layers outputs are not differentiable')
+            encoder_backward(ctx.mod, ctx.st, list(douts))
         ctx.st = None
-        return (None,) * (7 + ctx.n_params)
+        return (None,) * (6 + ctx.n_rest)
+
+
+def run_encoder_multi(mod, x, y, masks):
+    """masks: list of (video_idx, audio_idx) pairs -> list of outputs, all masks in ONE stack schedule."""
+    params = [p for p in mod.parameters() if p.requires_grad]
+    save = torch.is_grad_enabled() and len(params) > 0
+    flat = [m for pair in masks for m in pair]
+    out = EncoderFn.apply(mod, save, engine.Mode.current(), x, y, len(masks), *flat, *params)
+    return list(out)
 
 
 def run_encoder(mod, x, y, masks_v, masks_a):
-    params = [p for p in mod.parameters() if p.requires_grad]
-    save = torch.is_grad_enabled() and len(params) > 0
-    out = EncoderFn.apply(mod, save, engine.Mode.current(), x, y, masks_v, masks_a, *params)
-    if isinstance(out, tuple):
-        return list(out)
-    return out
+    out = run_encoder_multi(mod, x, y, [(masks_v, masks_a)])
+    if mod.out_layers is not None:
+        return out
+    return out[0]
+
+
+def merge_masks_enabled():
+    """AVJ_MERGE_MASKS=0 restores the reference's schedule (one backbone pass per mask) for A/B measurements."""
+    import os
+    return os.environ.get('AVJ_MERGE_MASKS', '1') != '0'
 
 
 # ================================================================================================
@@ -230,7 +261,7 @@ class BlocksFn(torch.autograd.Function):
         engine.require_cuda(x, 'block input')
         B, N, D = x.shape
         x = _f32c(x)
-        run = StackRun(B, N, D, blocks_mod[0].attn.num_heads, len(blocks_mod), mode, save, x.device,
+        run = StackRun([(B, N)], D, blocks_mod[0].attn.num_heads, len(blocks_mod), mode, save, x.device,
                        hidden=blocks_mod[0].mlp.fc1.out_features)
         engine.copy_rows(x.data_ptr(), F32, D, IDENTITY, run.x_in(0), F32, D, IDENTITY, B * N, D)
         sh = _shadows(owner)
@@ -268,176 +299,227 @@ class _PredState(object):
     pass
 
 
-def predictor_forward(mod, parts, mask_index, z_v, z_a, mcv, mca, mtv, mta, save, mode):
-    """parts = (embed_v, embed_a, tokens_v, tokens_a, pos_v, pos_a); the *_a entries are None for
-    the video-only predictor.  Token layout [ctx_v | tgt_v | ctx_a | tgt_a].
-    Returns (out [B, Ktv+Kta, D_enc] fp32, state)."""
+class _PredGroup(object):
+    """One mask of a predictor call: its tensors, index sets and row geometry inside the stack."""
+    __slots__ = ('mi', 'z_v', 'z_a', 'mcv', 'mca', 'mtv', 'mta', 'Kcv', 'Ktv', 'Kca', 'Kta', 'N', 'Kt', 'zc_v', 'zc_a', 't0')
+
+
+def predictor_forward(mod, parts, calls, save, mode):
+    """parts = (embed_v, embed_a, tokens_v, tokens_a, pos_v, pos_a); the *_a entries are None for the video-only
+    predictor.  `calls`: list of (mask_index, z_v, z_a, mcv, mca, mtv, mta), one per mask -- all of them run through ONE
+    variable-length stack (sequence group g = mask g).  Token layout inside a group: [ctx_v | tgt_v | ctx_a | tgt_a].
+    Returns ([out_g [B, Ktv+Kta, D_enc] fp32], state)."""
     embed_v, embed_a, tokens_v, tokens_a, pos_v, pos_a = parts
     if tokens_v is None:
         raise NotImplementedError('predictor without mask tokens (the diffusion branch) is not implemented; '
                                   'every AV-JEPA config sets use_mask_tokens=True')
-    engine.require_cuda(z_v, 'predictor context')
-    dev = z_v.device
-    B = z_v.shape[0]
-    mcv, mtv, mca, mta = _idx(mcv, dev), _idx(mtv, dev), _idx(mca, dev), _idx(mta, dev)
-    Kcv, Ktv = mcv.shape[1], mtv.shape[1]
-    Kca = mca.shape[1] if (mca is not None and z_a is not None) else 0
-    Kta = mta.shape[1] if mta is not None else 0
-    if z_v.shape[1] != Kcv or (z_a is not None and z_a.shape[1] != Kca):
-        raise ValueError(f'context token count {z_v.shape[1]} does not match the context mask ({Kcv})')
-    N = Kcv + Ktv + Kca + Kta
-    Kt = Ktv + Kta
+    engine.require_cuda(calls[0][1], 'predictor context')
+    dev = calls[0][1].device
+    B = calls[0][1].shape[0]
     De, Dp = embed_v.in_features, embed_v.out_features
     cd, s = mode.code, mode.size
-    mi = mask_index % len(tokens_v)
-    run = StackRun(B, N, Dp, mod.predictor_blocks[0].attn.num_heads, len(mod.predictor_blocks), mode, save, dev)
+    groups = []
+    for (mask_index, z_v, z_a, mcv, mca, mtv, mta) in calls:
+        g = _PredGroup()
+        g.mcv, g.mtv, g.mca, g.mta = _idx(mcv, dev), _idx(mtv, dev), _idx(mca, dev), _idx(mta, dev)
+        g.Kcv, g.Ktv = g.mcv.shape[1], g.mtv.shape[1]
+        g.Kca = g.mca.shape[1] if (g.mca is not None and z_a is not None) else 0
+        g.Kta = g.mta.shape[1] if g.mta is not None else 0
+        if z_v.shape[1] != g.Kcv or (z_a is not None and z_a.shape[1] != g.Kca):
+            raise ValueError(f'context token count {z_v.shape[1]} does not match the context mask ({g.Kcv})')
+        if z_v.shape[0] != B:
+            raise ValueError('all masks of one predictor call must share the batch size')
+        g.N = g.Kcv + g.Ktv + g.Kca + g.Kta
+        g.Kt = g.Ktv + g.Kta
+        g.mi = mask_index % len(tokens_v)
+        g.z_v, g.z_a = z_v, z_a
+        groups.append(g)
+    run = StackRun([(B, g.N) for g in groups], Dp, mod.predictor_blocks[0].attn.num_heads, len(mod.predictor_blocks), mode, save, dev)
     st = _PredState()
-    st.run, st.B, st.N, st.mode, st.mi = run, B, N, mode, mi
-    st.K = (Kcv, Ktv, Kca, Kta)
-    st.masks = (mcv, mtv, mca, mta)
+    st.run, st.B, st.mode, st.groups = run, B, mode, groups
     sh = _shadows(mod)
-    x0 = run.x_in(0)
-    # ---- context rows: x = embed(z) + pos[idx]  (bias and gathered pos fused in the epilogue)
-    keep, _, _, zmap_v = _rows_view(z_v)
-    st.zc_v = torch.empty((B * Kcv, De), dtype=mode.torch_dtype, device=dev)
-    engine.copy_rows(keep.data_ptr(), F32, De, zmap_v, st.zc_v.data_ptr(), cd, De, IDENTITY, B * Kcv, De)
     pv = _f32c(pos_v)
-    engine.gemm(mode, GEMM_NT, st.zc_v.data_ptr(), sh.weight_ptr(embed_v.weight, mode), x0, B * Kcv, Dp, De, De, De, Dp, F32,
-                bias=_ptr(embed_v.bias), pos=pv.data_ptr(), pos_idx=mcv.data_ptr(), pos_rows=pv.shape[1],
-                out_map=rowmap(Kcv, N, 0))
-    engine_keep = [keep, pv]
-    st.zc_a = None
-    pa = None
-    if Kca > 0:
-        keep_a, _, _, zmap_a = _rows_view(z_a)
-        st.zc_a = torch.empty((B * Kca, De), dtype=mode.torch_dtype, device=dev)
-        engine.copy_rows(keep_a.data_ptr(), F32, De, zmap_a, st.zc_a.data_ptr(), cd, De, IDENTITY, B * Kca, De)
-        pa = _f32c(pos_a)
-        engine.gemm(mode, GEMM_NT, st.zc_a.data_ptr(), sh.weight_ptr(embed_a.weight, mode), x0, B * Kca, Dp, De, De, De, Dp,
-                    F32, bias=_ptr(embed_a.bias), pos=pa.data_ptr(), pos_idx=mca.data_ptr(), pos_rows=pa.shape[1],
-                    out_map=rowmap(Kca, N, Kcv + Ktv))
-        engine_keep += [keep_a, pa]
-    elif Kta > 0:
-        pa = _f32c(pos_a)
-        engine_keep.append(pa)
-    # ---- target rows: mask token + pos[idx]
-    _cabi.call('avj_fill_mask_tokens', tokens_v[mi].data_ptr(), pv.data_ptr(), mtv.data_ptr(), x0, Dp,
-               rowmap(Ktv, N, Kcv), B * Ktv, Dp, stream())
-    if Kta > 0:
-        _cabi.call('avj_fill_mask_tokens', tokens_a[mi].data_ptr(), pa.data_ptr(), mta.data_ptr(), x0, Dp,
-                   rowmap(Kta, N, Kcv + Ktv + Kca), B * Kta, Dp, stream())
-    st.keep = engine_keep
-    # ---- blocks + predictor_norm, then project the target rows back to the encoder width
+    pa = _f32c(pos_a) if pos_a is not None else None
+    keep = [pv, pa]
+    t0 = 0
+    for gi, g in enumerate(groups):
+        x0, N = run.x0_rows(gi), g.N
+        # ---- context rows: x = embed(z) + pos[idx]  (bias and gathered pos fused in the epilogue)
+        zk, _, _, zmap_v = _rows_view(g.z_v)
+        g.zc_v = torch.empty((B * g.Kcv, De), dtype=mode.torch_dtype, device=dev)
+        engine.copy_rows(zk.data_ptr(), F32, De, zmap_v, g.zc_v.data_ptr(), cd, De, IDENTITY, B * g.Kcv, De)
+        engine.gemm(mode, GEMM_NT, g.zc_v.data_ptr(), sh.weight_ptr(embed_v.weight, mode), x0, B * g.Kcv, Dp, De, De, De, Dp, F32,
+                    bias=_ptr(embed_v.bias), pos=pv.data_ptr(), pos_idx=g.mcv.data_ptr(), pos_rows=pv.shape[1],
+                    out_map=rowmap(g.Kcv, N, 0))
+        keep.append(zk)
+        g.zc_a = None
+        if g.Kca > 0:
+            zka, _, _, zmap_a = _rows_view(g.z_a)
+            g.zc_a = torch.empty((B * g.Kca, De), dtype=mode.torch_dtype, device=dev)
+            engine.copy_rows(zka.data_ptr(), F32, De, zmap_a, g.zc_a.data_ptr(), cd, De, IDENTITY, B * g.Kca, De)
+            engine.gemm(mode, GEMM_NT, g.zc_a.data_ptr(), sh.weight_ptr(embed_a.weight, mode), x0, B * g.Kca, Dp, De, De, De, Dp,
+                        F32, bias=_ptr(embed_a.bias), pos=pa.data_ptr(), pos_idx=g.mca.data_ptr(), pos_rows=pa.shape[1],
+                        out_map=rowmap(g.Kca, N, g.Kcv + g.Ktv))
+            keep.append(zka)
+        # ---- target rows: mask token + pos[idx]
+        _cabi.call('avj_fill_mask_tokens', tokens_v[g.mi].data_ptr(), pv.data_ptr(), g.mtv.data_ptr(), x0, Dp,
+                   rowmap(g.Ktv, N, g.Kcv), B * g.Ktv, Dp, stream())
+        if g.Kta > 0:
+            _cabi.call('avj_fill_mask_tokens', tokens_a[g.mi].data_ptr(), pa.data_ptr(), g.mta.data_ptr(), x0, Dp,
+                       rowmap(g.Kta, N, g.Kcv + g.Ktv + g.Kca), B * g.Kta, Dp, stream())
+        g.z_v = g.z_a = None
+        g.t0 = t0                                   # first row of this group inside the packed target-row matrix
+        t0 += B * g.Kt
+    st.keep = keep
+    st.T = t0
+    # ---- blocks + predictor_norm over all groups at once, then project the target rows back to the encoder width
     blocks = [BlockW(b, sh, mode, False) for b in mod.predictor_blocks]
     norm = NormW(mod.predictor_norm, False)
-    st.ln_out = torch.empty((B * N, Dp), dtype=mode.torch_dtype, device=dev)
-    run.forward(blocks, norm, st.ln_out.data_ptr(), cd)
-    st.tgt_rows = torch.empty((B * Kt, Dp), dtype=mode.torch_dtype, device=dev)
-    engine.copy_rows(st.ln_out.data_ptr(), cd, Dp, rowmap(Ktv, N, Kcv), st.tgt_rows.data_ptr(), cd, Dp, rowmap(Ktv, Kt, 0),
-                     B * Ktv, Dp)
-    if Kta > 0:
-        engine.copy_rows(st.ln_out.data_ptr(), cd, Dp, rowmap(Kta, N, Kcv + Ktv + Kca), st.tgt_rows.data_ptr(), cd, Dp,
-                         rowmap(Kta, Kt, Ktv), B * Kta, Dp)
+    ln_out = torch.empty((run.R, Dp), dtype=mode.torch_dtype, device=dev)
+    run.forward(blocks, norm, ln_out.data_ptr(), cd)
+    st.tgt_rows = torch.empty((st.T, Dp), dtype=mode.torch_dtype, device=dev)      # [grp0 tgt_v|tgt_a per clip, grp1 ...]
     proj = mod.predictor_proj
-    out = torch.empty((B, Kt, De), dtype=torch.float32, device=dev)
-    engine.gemm(mode, GEMM_NT, st.tgt_rows.data_ptr(), sh.weight_ptr(proj.weight, mode), out.data_ptr(), B * Kt, De, Dp,
-                Dp, Dp, De, F32, bias=_ptr(proj.bias))
-    st.ln_out = None
+    outs = []
+    for gi, g in enumerate(groups):
+        src = ln_out.data_ptr() + run.row0[gi] * Dp * s
+        dst = st.tgt_rows.data_ptr() + g.t0 * Dp * s
+        engine.copy_rows(src, cd, Dp, rowmap(g.Ktv, g.N, g.Kcv), dst, cd, Dp, rowmap(g.Ktv, g.Kt, 0), B * g.Ktv, Dp)
+        if g.Kta > 0:
+            engine.copy_rows(src, cd, Dp, rowmap(g.Kta, g.N, g.Kcv + g.Ktv + g.Kca), dst, cd, Dp, rowmap(g.Kta, g.Kt, g.Ktv),
+                             B * g.Kta, Dp)
+        out = torch.empty((B, g.Kt, De), dtype=torch.float32, device=dev)
+        engine.gemm(mode, GEMM_NT, dst, sh.weight_ptr(proj.weight, mode), out.data_ptr(), B * g.Kt, De, Dp, Dp, Dp, De, F32,
+                    bias=_ptr(proj.bias))
+        outs.append(out)
     if not save:
-        st.zc_v = st.zc_a = st.tgt_rows = None
-    return out, st
+        st.tgt_rows = None
+        for g in groups:
+            g.zc_v = g.zc_a = None
+    return outs, st
 
 
-def predictor_backward(mod, parts, st, dout):
+def predictor_backward(mod, parts, st, douts):
+    """douts: one gradient per mask.  Returns [(dz_v, dz_a)] per mask."""
     embed_v, embed_a, tokens_v, tokens_a, pos_v, pos_a = parts
-    run, mode, B, N, mi = st.run, st.mode, st.B, st.N, st.mi
-    Kcv, Ktv, Kca, Kta = st.K
-    Kt = Ktv + Kta
+    run, mode, B, groups = st.run, st.mode, st.B, st.groups
     De, Dp = embed_v.in_features, embed_v.out_features
     cd, s = mode.code, mode.size
-    dev = dout.device
-    dout = _f32c(dout)
+    dev = next(d for d in douts if d is not None).device
     lib = _cabi.load()
     al = engine._align
-    kmax = max(Kcv, Kca, 1)
-    extra = (al(B * Kt * De * s) + al(B * Kt * Dp * s) + al(B * N * Dp * s) + al(B * kmax * Dp * s)
-             + 4 * lib.avj_colsum_ws_floats(B * max(Kt, kmax), max(De, Dp)) + (1 << 16))
+    kmax = max(max(g.Kcv, g.Kca, 1) for g in groups)
+    T, R = st.T, run.R
+    extra = (al(T * De * s) + al(T * Dp * s) + al(R * Dp * s) + al(B * kmax * Dp * s)
+             + 4 * lib.avj_colsum_ws_floats(max(T, B * kmax), max(De, Dp)) + (1 << 16))
     sc = engine.SCRATCH.get(run.scratch_bytes() + extra, dev)
     sh = _shadows(mod)
     proj = mod.predictor_proj
-    ws = sc.alloc(4 * lib.avj_colsum_ws_floats(B * max(Kt, kmax), max(De, Dp)))
-    # ---- predictor_proj backward on the target rows
-    dout_c = sc.alloc(B * Kt * De * s)
-    engine.copy_rows(dout.data_ptr(), F32, De, IDENTITY, dout_c, cd, De, IDENTITY, B * Kt, De)
+    ws = sc.alloc(4 * lib.avj_colsum_ws_floats(max(T, B * kmax), max(De, Dp)))
+    # ---- predictor_proj backward on the packed target rows of ALL masks: one bias colsum per mask (fp32 inputs live
+    # in separate tensors), then ONE wgrad and ONE dgrad GEMM
+    dout_c = sc.alloc(T * De * s)
     gpw, gpb = engine.grad_ptr(proj.weight), engine.grad_ptr(proj.bias)
-    if gpb is not None:
-        engine.colsum(dout.data_ptr(), F32, De, IDENTITY, gpb, B * Kt, De, ws)
+    for g, d in zip(groups, douts):
+        rows = B * g.Kt
+        dst = dout_c + g.t0 * De * s
+        if d is None:
+            engine.memset0(dst, rows * De * s)
+            continue
+        d = _f32c(d)
+        engine.copy_rows(d.data_ptr(), F32, De, IDENTITY, dst, cd, De, IDENTITY, rows, De)
+        if gpb is not None:
+            engine.colsum(d.data_ptr(), F32, De, IDENTITY, gpb, rows, De, ws)
     if gpw is not None:
-        engine.gemm(mode, GEMM_TN, dout_c, st.tgt_rows.data_ptr(), gpw, De, Dp, B * Kt, De, Dp, Dp, F32, accumulate=1)
-    d_tgt = sc.alloc(B * Kt * Dp * s)
-    engine.gemm(mode, GEMM_NN, dout_c, sh.weight_ptr(proj.weight, mode), d_tgt, B * Kt, Dp, De, De, Dp, Dp, cd)
+        engine.gemm(mode, GEMM_TN, dout_c, st.tgt_rows.data_ptr(), gpw, De, Dp, T, De, Dp, Dp, F32, accumulate=1)
+    d_tgt = sc.alloc(T * Dp * s)
+    engine.gemm(mode, GEMM_NN, dout_c, sh.weight_ptr(proj.weight, mode), d_tgt, T, Dp, De, De, Dp, Dp, cd)
     # ---- scatter into the gradient of the predictor_norm output (zero on context rows)
-    d_ln = sc.alloc(B * N * Dp * s)
-    engine.memset0(d_ln, B * N * Dp * s)
-    engine.copy_rows(d_tgt, cd, Dp, rowmap(Ktv, Kt, 0), d_ln, cd, Dp, rowmap(Ktv, N, Kcv), B * Ktv, Dp)
-    if Kta > 0:
-        engine.copy_rows(d_tgt, cd, Dp, rowmap(Kta, Kt, Ktv), d_ln, cd, Dp, rowmap(Kta, N, Kcv + Ktv + Kca), B * Kta, Dp)
+    d_ln = sc.alloc(R * Dp * s)
+    engine.memset0(d_ln, R * Dp * s)
+    for gi, g in enumerate(groups):
+        src = d_tgt + g.t0 * Dp * s
+        dst = d_ln + run.row0[gi] * Dp * s
+        engine.copy_rows(src, cd, Dp, rowmap(g.Ktv, g.Kt, 0), dst, cd, Dp, rowmap(g.Ktv, g.N, g.Kcv), B * g.Ktv, Dp)
+        if g.Kta > 0:
+            engine.copy_rows(src, cd, Dp, rowmap(g.Kta, g.Kt, g.Ktv), dst, cd, Dp, rowmap(g.Kta, g.N, g.Kcv + g.Ktv + g.Kca),
+                             B * g.Kta, Dp)
     blocks = [BlockW(b, sh, mode, True) for b in mod.predictor_blocks]
     norm = NormW(mod.predictor_norm, True)
-    dx0 = run.backward(blocks, norm, d_ln, cd, sc)
-    # ---- mask-token gradients: column sums over the target rows
-    gt = engine.grad_ptr(tokens_v[mi])
-    if gt is not None:
-        engine.colsum(dx0, F32, Dp, rowmap(Ktv, N, Kcv), gt, B * Ktv, Dp, ws)
-    if Kta > 0:
-        gt = engine.grad_ptr(tokens_a[mi])
-        if gt is not None:
-            engine.colsum(dx0, F32, Dp, rowmap(Kta, N, Kcv + Ktv + Kca), gt, B * Kta, Dp, ws)
-    # ---- context embeddings
+    dx0_all = run.backward(blocks, norm, d_ln, cd, sc)
     dctx = sc.alloc(B * kmax * Dp * s)
-    grads_z = []
-    for (K, off, zc, emb) in ((Kcv, 0, st.zc_v, embed_v), (Kca, Kcv + Ktv, st.zc_a, embed_a)):
-        if K == 0 or emb is None or zc is None:
-            grads_z.append(None)
-            continue
-        rm = rowmap(K, N, off)
-        gw, gb = engine.grad_ptr(emb.weight), engine.grad_ptr(emb.bias)
-        if gb is not None:
-            engine.colsum(dx0, F32, Dp, rm, gb, B * K, Dp, ws)
-        engine.copy_rows(dx0, F32, Dp, rm, dctx, cd, Dp, IDENTITY, B * K, Dp)
-        if gw is not None:
-            engine.gemm(mode, GEMM_TN, dctx, zc.data_ptr(), gw, Dp, De, B * K, Dp, De, De, F32, accumulate=1)
-        dz = torch.empty((B, K, De), dtype=torch.float32, device=dev)
-        engine.gemm(mode, GEMM_NN, dctx, sh.weight_ptr(emb.weight, mode), dz.data_ptr(), B * K, De, Dp, Dp, De, De, F32)
-        grads_z.append(dz)
-    return grads_z
+    grads = []
+    for gi, g in enumerate(groups):
+        dx0 = dx0_all + run.row0[gi] * Dp * 4
+        N = g.N
+        # ---- mask-token gradients: column sums over the target rows
+        gt = engine.grad_ptr(tokens_v[g.mi])
+        if gt is not None:
+            engine.colsum(dx0, F32, Dp, rowmap(g.Ktv, N, g.Kcv), gt, B * g.Ktv, Dp, ws)
+        if g.Kta > 0:
+            gt = engine.grad_ptr(tokens_a[g.mi])
+            if gt is not None:
+                engine.colsum(dx0, F32, Dp, rowmap(g.Kta, N, g.Kcv + g.Ktv + g.Kca), gt, B * g.Kta, Dp, ws)
+        # ---- context embeddings
+        gz = []
+        for (K, off, zc, emb) in ((g.Kcv, 0, g.zc_v, embed_v), (g.Kca, g.Kcv + g.Ktv, g.zc_a, embed_a)):
+            if K == 0 or emb is None or zc is None:
+                gz.append(None)
+                continue
+            rm = rowmap(K, N, off)
+            gw, gb = engine.grad_ptr(emb.weight), engine.grad_ptr(emb.bias)
+            if gb is not None:
+                engine.colsum(dx0, F32, Dp, rm, gb, B * K, Dp, ws)
+            engine.copy_rows(dx0, F32, Dp, rm, dctx, cd, Dp, IDENTITY, B * K, Dp)
+            if gw is not None:
+                engine.gemm(mode, GEMM_TN, dctx, zc.data_ptr(), gw, Dp, De, B * K, Dp, De, De, F32, accumulate=1)
+            dz = torch.empty((B, K, De), dtype=torch.float32, device=dev)
+            engine.gemm(mode, GEMM_NN, dctx, sh.weight_ptr(emb.weight, mode), dz.data_ptr(), B * K, De, Dp, Dp, De, De, F32)
+            gz.append(dz)
+        grads.append(tuple(gz))
+    return grads
 
 
 class PredictorFn(torch.autograd.Function):
+    """autograd node for one predictor call over n masks; tensor inputs are (z_v, z_a) per mask, then the module's
+    parameters (listed for autograd's dependency tracking only)."""
 
     @staticmethod
-    def forward(ctx, mod, parts, save, mode, mask_index, z_v, z_a, mcv, mca, mtv, mta, *params):
-        out, st = predictor_forward(mod, parts, mask_index, z_v, z_a, mcv, mca, mtv, mta, save, mode)
-        ctx.mod, ctx.parts, ctx.st, ctx.n_params = mod, parts, st, len(params)
-        ctx.za_shape = None if z_a is None else tuple(z_a.shape)
-        return out
+    def forward(ctx, mod, parts, save, mode, meta, *rest):
+        n = len(meta)
+        zs = rest[:2 * n]
+        calls = [(meta[i][0], zs[2 * i], zs[2 * i + 1]) + tuple(meta[i][1:]) for i in range(n)]
+        outs, st = predictor_forward(mod, parts, calls, save, mode)
+        ctx.mod, ctx.parts, ctx.st, ctx.n, ctx.n_rest = mod, parts, st, n, len(rest)
+        ctx.za_shapes = [None if zs[2 * i + 1] is None else tuple(zs[2 * i + 1].shape) for i in range(n)]
+        return tuple(outs)
 
     @staticmethod
-    def backward(ctx, dout):
-        dz_v = dz_a = None
-        if dout is not None:
-            dz_v, dz_a = predictor_backward(ctx.mod, ctx.parts, ctx.st, dout)
+    def backward(ctx, *douts):
+        n = ctx.n
+        gz = [None] * (2 * n)
+        if any(d is not None for d in douts):
+            grads = predictor_backward(ctx.mod, ctx.parts, ctx.st, list(douts))
             from avjepa_b200 import dist as avj_dist
             sync = avj_dist.active_sync()
             if sync is not None:
                 sync.on_backward_done('predictor', ctx.mod)
-            if dz_a is None and ctx.za_shape is not None and ctx.needs_input_grad[6]:
-                dz_a = torch.zeros(ctx.za_shape, dtype=torch.float32, device=dout.device)
+            dev = next(d for d in douts if d is not None).device
+            for i, (dz_v, dz_a) in enumerate(grads):
+                if dz_a is None and ctx.za_shapes[i] is not None and ctx.needs_input_grad[5 + 2 * i + 1]:
+                    dz_a = torch.zeros(ctx.za_shapes[i], dtype=torch.float32, device=dev)
+                gz[2 * i], gz[2 * i + 1] = dz_v, dz_a
         ctx.st = None
-        return (None, None, None, None, None, dz_v, dz_a, None, None, None, None) + (None,) * ctx.n_params
+        return (None, None, None, None, None) + tuple(gz) + (None,) * (ctx.n_rest - 2 * n)
+
+
+def run_predictor_multi(mod, parts, calls):
+    """calls: list of (mask_index, z_v, z_a, mcv, mca, mtv, mta) -> list of outputs, all masks in ONE stack schedule."""
+    params = [p for p in mod.parameters() if p.requires_grad]
+    save = torch.is_grad_enabled() and (len(params) > 0 or any(c[1].requires_grad for c in calls))
+    meta = tuple((c[0], c[3], c[4], c[5], c[6]) for c in calls)
+    zs = [t for c in calls for t in (c[1], c[2])]
+    return list(PredictorFn.apply(mod, parts, save, engine.Mode.current(), meta, *zs, *params))
 
 
 def run_predictor(mod, parts, mask_index, z_v, z_a, mcv, mca, mtv, mta):
-    params = [p for p in mod.parameters() if p.requires_grad]
-    save = torch.is_grad_enabled() and (len(params) > 0 or z_v.requires_grad)
-    return PredictorFn.apply(mod, parts, save, engine.Mode.current(), mask_index, z_v, z_a, mcv, mca, mtv, mta, *params)
+    return run_predictor_multi(mod, parts, [(mask_index, z_v, z_a, mcv, mca, mtv, mta)])[0]

@@ -23,19 +23,46 @@ static inline avj_epilogue epi(int out_dtype) {
   return e;
 }
 
+// groups of equal-length sequences inside the token matrix (avj_stack.n_seg / seg_B / seg_N)
+struct Segs {
+  int n; int B[AVJ_MAX_SEGMENTS]; int N[AVJ_MAX_SEGMENTS]; int64_t row0[AVJ_MAX_SEGMENTS]; int64_t lse0[AVJ_MAX_SEGMENTS]; int64_t R;
+};
+static int make_segs(const avj_stack* s, Segs* g) {
+  g->n = s->n_seg > 0 ? s->n_seg : 1;
+  AVJ_CHECK(g->n <= AVJ_MAX_SEGMENTS, "avj_stack: %d segments (max %d)", g->n, AVJ_MAX_SEGMENTS);
+  int64_t r = 0, l = 0;
+  for (int i = 0; i < g->n; ++i) {
+    g->B[i] = s->n_seg > 0 ? s->seg_B[i] : s->B;
+    g->N[i] = s->n_seg > 0 ? s->seg_N[i] : s->N;
+    AVJ_CHECK(g->B[i] >= 0 && g->N[i] >= 0, "avj_stack: negative segment shape");
+    g->row0[i] = r; g->lse0[i] = l;
+    r += (int64_t)g->B[i] * g->N[i];
+    l += (int64_t)g->B[i] * s->H * g->N[i];
+  }
+  AVJ_CHECK(r < (1ll << 31), "avj_stack: %lld rows overflow int32", (long long)r);
+  g->R = r;
+  return 0;
+}
+static inline size_t esize(int dtype) { return dtype == AVJ_BF16 ? 2 : 4; }
+
 extern "C" int avj_stack_forward(const avj_stack* s, const avj_layer* L, void* stream) {
   AVJ_CHECK(s && L, "avj_stack_forward: NULL argument");
-  const int R = s->B * s->N, D = s->D, Hd = s->hidden, cd = s->dtype;
+  Segs g;
+  RC(make_segs(s, &g));
+  const int R = (int)g.R, D = s->D, Hd = s->hidden, cd = s->dtype;
   AVJ_CHECK(s->H > 0 && D % s->H == 0, "avj_stack_forward: D=%d not divisible by heads=%d", D, s->H);
   const int hd = D / s->H;
   const float scale = 1.0f / sqrtf((float)hd);
+  const size_t es = esize(cd);
   for (int i = 0; i < s->L; ++i) {
     const avj_layer& w = L[i];
     RC(avj_layernorm_fwd(w.x, w.n1.w, w.n1.b, w.h1, cd, w.mean1, w.rstd1, R, D, w.n1.eps, stream));
     avj_epilogue e = epi(cd);
     e.bias = w.qkv.b;
     RC(avj_gemm(cd, AVJ_GEMM_NT, w.h1, w.qkv.w, w.qkv_act, R, 3 * D, D, D, D, 3 * D, &e, stream));
-    RC(avj_attention_fwd(cd, w.qkv_act, w.o, w.lse, s->B, s->N, s->H, hd, scale, stream));
+    for (int k = 0; k < g.n; ++k)
+      RC(avj_attention_fwd(cd, (const char*)w.qkv_act + g.row0[k] * 3 * D * es, (char*)w.o + g.row0[k] * D * es, w.lse + g.lse0[k],
+                           g.B[k], g.N[k], s->H, hd, scale, stream));
     e = epi(AVJ_F32);
     e.bias = w.proj.b; e.residual = w.x;
     RC(avj_gemm(cd, AVJ_GEMM_NT, w.o, w.proj.w, w.x1, R, D, D, D, D, D, &e, stream));
@@ -52,9 +79,12 @@ extern "C" int avj_stack_forward(const avj_stack* s, const avj_layer* L, void* s
 
 extern "C" int avj_stack_backward(const avj_stack* s, const avj_layer* L, const avj_stack_scratch* sc, void* stream) {
   AVJ_CHECK(s && L && sc, "avj_stack_backward: NULL argument");
-  const int R = s->B * s->N, D = s->D, Hd = s->hidden, cd = s->dtype;
+  Segs g;
+  RC(make_segs(s, &g));
+  const int R = (int)g.R, D = s->D, Hd = s->hidden, cd = s->dtype;
   const int hd = D / s->H;
   const float scale = 1.0f / sqrtf((float)hd);
+  const size_t es = esize(cd);
   const avj_rowmap ident = {0, 0, 0};
   float* cur = sc->dxa;
   float* nxt = sc->dxb;
@@ -89,7 +119,10 @@ extern "C" int avj_stack_backward(const avj_stack* s, const avj_layer* L, const 
     }
     e = epi(cd);
     RC(avj_gemm(cd, AVJ_GEMM_NN, sc->dx_lp, w.proj.w, sc->d_o, R, D, D, D, D, D, &e, stream));
-    RC(avj_attention_bwd(cd, w.qkv_act, w.o, sc->d_o, w.lse, sc->d_qkv, sc->ws, s->B, s->N, s->H, hd, scale, stream));
+    for (int k = 0; k < g.n; ++k)
+      RC(avj_attention_bwd(cd, (const char*)w.qkv_act + g.row0[k] * 3 * D * es, (const char*)w.o + g.row0[k] * D * es,
+                           (const char*)sc->d_o + g.row0[k] * D * es, w.lse + g.lse0[k], (char*)sc->d_qkv + g.row0[k] * 3 * D * es,
+                           sc->ws, g.B[k], g.N[k], s->H, hd, scale, stream));
     if (w.qkv.gb && w.fc1.gb) {
       RC(avj_colsum2(sc->d_qkv, 3 * D, 3 * D, w.qkv.gb, sc->d_hid, Hd, Hd, w.fc1.gb, cd, R, sc->ws, stream));
     } else {

@@ -228,13 +228,31 @@ class Shadows(object):
 # transformer stack
 # ----------------------------------------------------------------------------------------------
 class StackRun(object):
-    """One forward (and optionally backward) of L pre-LN blocks + final LayerNorm over a token
-    matrix [B*N, D].  Restates Block.forward / Attention.forward / MLP.forward of the reference
-    (src/models/utils/modules.py:114-120, :61-78, :30-36) as an explicit kernel schedule."""
+    """One forward (and optionally backward) of L pre-LN blocks + final LayerNorm over a token matrix [R, D].
+    Restates Block.forward / Attention.forward / MLP.forward of the reference
+    (src/models/utils/modules.py:114-120, :61-78, :30-36) as an explicit kernel schedule.
 
-    def __init__(self, B, N, D, heads, depth, mode, save, device, hidden=None):
-        self.B, self.N, self.D, self.H, self.L = B, N, D, heads, depth
-        self.R = B * N
+    The token matrix is a VARIABLE-LENGTH batch: `segs` = [(B_0, N_0), (B_1, N_1), ...] groups of B_g sequences of N_g
+    tokens each, rows of group g starting at ``row0[g]``.  The reference's MultiMask wrappers run the whole backbone
+    once per mask (src/models/utils/multimask.py:37-46,55-71); here both masks travel through ONE schedule -- every
+    Linear / LayerNorm / column-sum is a single launch over all rows, attention runs per group."""
+
+    def __init__(self, segs, D, heads, depth, mode, save, device, hidden=None):
+        if isinstance(segs, tuple) and len(segs) == 2 and not isinstance(segs[0], (tuple, list)):
+            segs = [segs]
+        self.segs = [(int(b), int(n)) for b, n in segs]
+        if len(self.segs) > _cabi.MAX_SEGMENTS:
+            raise _cabi.AvjError(f'{len(self.segs)} sequence groups in one stack (max {_cabi.MAX_SEGMENTS})')
+        self.B, self.N = self.segs[0]                       # single-group callers
+        self.D, self.H, self.L = D, heads, depth
+        self.row0, self.lse0 = [], []
+        r = l = 0
+        for b, n in self.segs:
+            self.row0.append(r)
+            self.lse0.append(l)
+            r += b * n
+            l += b * heads * n
+        self.R = r
         self.hd = D // heads
         self.Hd = hidden if hidden is not None else 4 * D
         self.mode, self.save, self.device = mode, save, device
@@ -242,7 +260,7 @@ class StackRun(object):
         # per-layer saved layout (byte offsets)
         o, lay = 0, {}
         for name, nbytes in (('x', R * D * 4), ('mean1', R * 4), ('rstd1', R * 4), ('h1', R * D * s),
-                             ('qkv', R * 3 * D * s), ('o', R * D * s), ('lse', B * heads * N * 4),
+                             ('qkv', R * 3 * D * s), ('o', R * D * s), ('lse', l * 4),
                              ('x1', R * D * 4), ('mean2', R * 4), ('rstd2', R * 4), ('h2', R * D * s),
                              ('pre', R * self.Hd * s), ('act', R * self.Hd * s)):
             lay[name] = o
@@ -271,16 +289,25 @@ class StackRun(object):
     def x_out(self, layer):
         return self.x_in(layer + 1)
 
+    def x0_rows(self, g):
+        """Pointer of the first fp32 input row of group g (where the embedding kernels write)."""
+        return self.x_in(0) + self.row0[g] * self.D * 4
+
+    def attn_ws_floats(self):
+        lib = _cabi.load()
+        return max(lib.avj_attention_bwd_ws_floats(b, n, self.H, self.hd) for b, n in self.segs)
+
     # -- forward ---------------------------------------------------------------------------
     def forward_layer(self, i, w):
         """x_{i+1} = Block_i(x_i): LN1 -> qkv -> attention -> proj(+x) -> LN2 -> fc1/GELU -> fc2(+x1)."""
-        m, R, D, Hd, cd = self.mode, self.R, self.D, self.Hd, self.mode.code
+        m, R, D, Hd, cd, s = self.mode, self.R, self.D, self.Hd, self.mode.code, self.mode.size
         scale = float(self.hd ** -0.5)
         x, x1, xo = self.x_in(i), self.slot(i, 'x1'), self.x_out(i)
         layernorm_fwd(x, w.n1.w, w.n1.b, self.slot(i, 'h1'), cd, self.slot(i, 'mean1'), self.slot(i, 'rstd1'), R, D, w.n1.eps)
         gemm(m, GEMM_NT, self.slot(i, 'h1'), w.qkv.w, self.slot(i, 'qkv'), R, 3 * D, D, D, D, 3 * D, cd, bias=w.qkv.b)
-        _cabi.call('avj_attention_fwd', cd, self.slot(i, 'qkv'), self.slot(i, 'o'), self.slot(i, 'lse'),
-                   self.B, self.N, self.H, self.hd, scale, stream())
+        for (b, n), r0, l0 in zip(self.segs, self.row0, self.lse0):
+            _cabi.call('avj_attention_fwd', cd, self.slot(i, 'qkv') + r0 * 3 * D * s, self.slot(i, 'o') + r0 * D * s,
+                       self.slot(i, 'lse') + l0 * 4, b, n, self.H, self.hd, scale, stream())
         gemm(m, GEMM_NT, self.slot(i, 'o'), w.proj.w, x1, R, D, D, D, D, D, F32, bias=w.proj.b, residual=x)
         layernorm_fwd(x1, w.n2.w, w.n2.b, self.slot(i, 'h2'), cd, self.slot(i, 'mean2'), self.slot(i, 'rstd2'), R, D, w.n2.eps)
         gemm(m, GEMM_NT, self.slot(i, 'h2'), w.fc1.w, self.slot(i, 'act'), R, Hd, D, D, D, Hd, cd, bias=w.fc1.b,
@@ -289,7 +316,11 @@ class StackRun(object):
 
     # -- whole-stack C schedule --------------------------------------------------------------
     def _stack_desc(self):
-        return _cabi.Stack(self.mode.code, self.B, self.N, self.D, self.H, self.Hd, self.L)
+        d = _cabi.Stack(self.mode.code, self.B, self.N, self.D, self.H, self.Hd, self.L)
+        d.n_seg = len(self.segs)
+        for g, (b, n) in enumerate(self.segs):
+            d.seg_B[g], d.seg_N[g] = b, n
+        return d
 
     def _layer_array(self, blocks):
         """ctypes array of avj_layer: weight pointers + this run's activation slots."""
@@ -310,34 +341,46 @@ class StackRun(object):
             l.pre = sl(i, 'pre') if self.save else None
         return arr
 
+    def _per_group(self, ptrs):
+        """Normalise an output / gradient pointer argument: one pointer for all R rows (contiguous) -> [(ptr, row0,
+        rows)], or a list with one pointer per group."""
+        if isinstance(ptrs, (list, tuple)):
+            assert len(ptrs) == len(self.segs)
+            return [(p, r0, b * n) for p, r0, (b, n) in zip(ptrs, self.row0, self.segs)]
+        return [(ptrs, 0, self.R)]
+
     def forward(self, blocks, norm, out_ptr, out_dtype):
-        """blocks: list[BlockW]; norm: NormW or None.  Writes LN(x_L) to out_ptr."""
-        R, D = self.R, self.D
+        """blocks: list[BlockW]; norm: NormW or None.  Writes LN(x_L) to `out_ptr` -- one pointer for all rows, or a
+        list with one (contiguous) destination per sequence group."""
+        D = self.D
         if self.L > 0:
             desc, arr = self._stack_desc(), self._layer_array(blocks)
             _cabi.call('avj_stack_forward', C.byref(desc), arr, stream())
         self.x_last = self.x_in(self.L)
-        if norm is not None:
-            layernorm_fwd(self.x_last, norm.w, norm.b, out_ptr, out_dtype, self.mean_f, self.rstd_f, R, D, norm.eps)
-        else:
-            copy_rows(self.x_last, F32, D, _cabi.IDENTITY, out_ptr, out_dtype, D, _cabi.IDENTITY, R, D)
+        for p, r0, rows in self._per_group(out_ptr):
+            if rows == 0:
+                continue
+            if norm is not None:
+                layernorm_fwd(self.x_last + r0 * D * 4, norm.w, norm.b, p, out_dtype, self.mean_f + r0 * 4, self.rstd_f + r0 * 4,
+                              rows, D, norm.eps)
+            else:
+                copy_rows(self.x_last + r0 * D * 4, F32, D, _cabi.IDENTITY, p, out_dtype, D, _cabi.IDENTITY, rows, D)
 
     # -- backward --------------------------------------------------------------------------
     def scratch_bytes(self):
         R, D, Hd, s = self.R, self.D, self.Hd, self.mode.size
         per = 2 * _align(R * D * 4) + _align(R * D * s) + _align(R * Hd * s) + _align(R * 3 * D * s) + 2 * _align(R * D * s)
         ws = max(_cabi.load().avj_layernorm_bwd_ws_floats(R, D), _cabi.load().avj_colsum_ws_floats(R, 3 * D + Hd),
-                 _cabi.load().avj_attention_bwd_ws_floats(self.B, self.N, self.H, self.hd)) * 4
+                 self.attn_ws_floats()) * 4
         return per + _align(ws) + (1 << 16)
 
     def backward(self, blocks, norm, dy_ptr, dy_dtype, sc, layer_events=None):
-        """dy: gradient wrt LN(x_L) output, [R, D] contiguous in dy_dtype.  `sc` is a scratch
-        Arena with at least scratch_bytes().  Returns the pointer of d x_0 (fp32, in scratch).
+        """dy: gradient wrt the LN(x_L) output in dy_dtype -- one pointer ([R, D] contiguous) or one per sequence
+        group.  `sc` is a scratch Arena with at least scratch_bytes().  Returns the pointer of d x_0 (fp32, in scratch).
         `layer_events`: optional list of L torch.cuda.Event; event i is recorded (by the C schedule, on the
         launch stream) when layer i's parameter gradients are final for this call."""
         assert self.save, 'backward needs a forward run with save=True'
         m, R, D, Hd, cd, s = self.mode, self.R, self.D, self.Hd, self.mode.code, self.mode.size
-        scale = float(self.hd ** -0.5)
         dxa = sc.alloc(R * D * 4)          # fp32 residual-gradient ping
         dxb = sc.alloc(R * D * 4)          # pong
         dx_lp = sc.alloc(R * D * s)        # compute-dtype copy feeding the GEMMs
@@ -347,14 +390,19 @@ class StackRun(object):
         d_o = sc.alloc(R * D * s)
         lib = _cabi.load()
         ws = sc.alloc(4 * max(lib.avj_layernorm_bwd_ws_floats(R, D), lib.avj_colsum_ws_floats(R, 3 * D + Hd),
-                              lib.avj_attention_bwd_ws_floats(self.B, self.N, self.H, self.hd)))
+                              self.attn_ws_floats()))
         cur, nxt = dxa, dxb
-        if norm is not None:
-            layernorm_bwd(dy_ptr, dy_dtype, self.x_in(self.L), norm.w, self.mean_f, self.rstd_f, None, cur, dx_lp, cd,
-                          norm.gw, norm.gb, ws, R, D)
-        else:
-            copy_rows(dy_ptr, dy_dtype, D, _cabi.IDENTITY, cur, F32, D, _cabi.IDENTITY, R, D)
-            copy_rows(dy_ptr, dy_dtype, D, _cabi.IDENTITY, dx_lp, cd, D, _cabi.IDENTITY, R, D)
+        esz = 4 if dy_dtype == F32 else 2
+        for p, r0, rows in self._per_group(dy_ptr):
+            if rows == 0:
+                continue
+            if norm is not None:
+                layernorm_bwd(p, dy_dtype, self.x_in(self.L) + r0 * D * 4, norm.w, self.mean_f + r0 * 4, self.rstd_f + r0 * 4, None,
+                              cur + r0 * D * 4, dx_lp + r0 * D * s, cd, norm.gw, norm.gb, ws, rows, D)
+            else:
+                copy_rows(p, dy_dtype, D, _cabi.IDENTITY, cur + r0 * D * 4, F32, D, _cabi.IDENTITY, rows, D)
+                copy_rows(p, dy_dtype, D, _cabi.IDENTITY, dx_lp + r0 * D * s, cd, D, _cabi.IDENTITY, rows, D)
+        del esz
         if self.L > 0:
             desc, arr = self._stack_desc(), self._layer_array(blocks)
             ev_arr = None

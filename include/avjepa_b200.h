@@ -224,9 +224,19 @@ typedef struct avj_layer {
   float* x1; float* mean2; float* rstd2; void* h2; void* pre; void* act;
   float* x_out;            /* residual stream after this block (= next layer's x)          */
 } avj_layer;
+#define AVJ_MAX_SEGMENTS 8
 typedef struct avj_stack {
   int32_t dtype;           /* AVJ_F32 / AVJ_BF16: operand dtype of GEMMs and attention      */
   int32_t B, N, D, H, hidden, L;
+  /* Variable-length batch: n_seg > 0 -> the token matrix is the concatenation of n_seg groups, group g holding
+   * seg_B[g] sequences of seg_N[g] tokens each (rows of group g start at sum_{j<g} seg_B[j]*seg_N[j]); B and N are
+   * ignored.  The Linear / LayerNorm kernels see one [sum B*N, D] matrix -- ONE launch per Linear for all groups
+   * (the reference's MultiMask wrappers run the whole backbone once per mask, src/models/utils/multimask.py:37-46,
+   * 55-71) -- and attention runs per group.  lse of group g starts at sum_{j<g} seg_B[j]*H*seg_N[j] floats.
+   * n_seg == 0 -> one group (B, N). */
+  int32_t n_seg;
+  int32_t seg_B[AVJ_MAX_SEGMENTS];
+  int32_t seg_N[AVJ_MAX_SEGMENTS];
 } avj_stack;
 typedef struct avj_stack_scratch {
   float* dxa; float* dxb;  /* fp32 [B*N, D] residual-gradient ping/pong; dxa holds d x_L on entry

@@ -446,7 +446,11 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-parity', action='store_true', help='skip the B=2 oracle parity block')
     ap.add_argument('--no-reference-gpu', action='store_true', help='skip the reference-on-GPU competitor leg')
-    ap.add_argument('--same-masks', action='store_true', help='N>1: every rank draws the SAME mask lengths (A/B of straggler skew)')
+    ap.add_argument('--per-rank-masks', action='store_true',
+                    help='N>1: every rank seeds its mask collator differently (lengths differ across ranks -> straggler skew). '
+                         'Default: identical collator streams on all ranks, which is what the reference does -- it seeds every '
+                         'rank with the same meta.seed (app/avjepa/train.py:164-165), so the DataLoader workers of all ranks '
+                         'draw the same block positions')
     ap.add_argument('--frozen-forward', action='store_true', help='BASELINE config 5: no-grad encoder forward at N=1664')
     ap.add_argument('--fp32', action='store_true', help='fp32 check mode instead of bf16')
     ap.add_argument('--profile-only', action='store_true',
@@ -495,7 +499,7 @@ def main():
     host_clips = torch.randn(B, 3, 16, 224, 224, generator=g).pin_memory()
     host_asgram = (-80.0 * torch.rand(B, 1, 128, 192, generator=g)).pin_memory()
     n_sets = 2 * (K + W) + 1
-    mask_sets = sample_masks(n_sets, B, seed=234 + (0 if args.same_masks else rank))
+    mask_sets = sample_masks(n_sets, B, seed=234 + (rank if args.per_rank_masks else 0))
     host_masks = [tuple([m.pin_memory() for m in grp] for grp in s) for s in mask_sets]
     lens = [[(s[0][i].shape[1], s[1][i].shape[1], s[2][i].shape[1], s[3][i].shape[1]) for i in range(2)] for s in mask_sets]
 
@@ -605,7 +609,7 @@ def main():
         config=dict(workload=f'{args.model} AV-JEPA pretrain step (configs/pretrain/vitl16.yaml shape), batch {B}/GPU, '
                              f'16x224x224 video + 128x192 log-mel, 2 multiblock masks, predictor depth {PRED_DEPTH}',
                     parallelism=f'dp{world}', l2='inputs+weights (>1.5 GB/step) exceed the 126 MB L2; no explicit flush',
-                    masks='same lengths on every rank' if args.same_masks else 'per-rank collator draws (lengths differ across ranks)',
+                    masks='per-rank collator seeds (lengths differ across ranks)' if args.per_rank_masks else 'collator seeded with meta.seed on every rank, like the reference (same mask lengths on all ranks)',
                     clips_per_s_per_gpu=clips_per_s / world,
                     step_tflops_per_gpu=step_tflops, frac_of_bf16_peak=step_tflops / peaks['bf16_sustained'],
                     flops_per_clip=flops_clip, loss=loss_res),

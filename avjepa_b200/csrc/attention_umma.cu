@@ -52,10 +52,11 @@ template <int HDP, bool TS> struct UaSmem {
 // the hardware); TMA = false: the loader warp gathers 16-byte chunks with cp.async and pads in smem.
 // POLY: every fourth pair of scores takes ua_exp2_poly (FMA pipe) instead of MUFU ex2.
 // TS: P goes to tensor memory (packed bf16, columns [192, 256)) and is the A operand of the PV MMA from there.
-template <int HDP, bool TMA, bool POLY, bool TS>
+// ILV: exp2 / row-sum / pack of the softmax interleaved group-wise through a value-neutral dependency (see below).
+template <int HDP, bool TMA, bool POLY, bool TS, bool ILV>
 __global__ void __launch_bounds__(UA_THREADS, 2)
 fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restrict__ qkv, bf16* __restrict__ out,
-                   float* __restrict__ lse, int N, int H, int hd, float scale_log2) {
+                   float* __restrict__ lse, int N, int H, int hd, float scale_log2, uint32_t zero_u) {
   extern __shared__ __align__(1024) uint8_t ua_raw[];
   const uint32_t base = ua_smem(ua_raw);
   using L = UaSmem<HDP, TS>;
@@ -199,6 +200,7 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
     const uint32_t t_s = tmem + ((uint32_t)(q * 32) << 16);
     const uint32_t t_o = t_s + UA_O_COL;
     float m = -INFINITY, l = 0.f;
+    // zero_u: kernel argument, always 0 -- a zero the compiler cannot see through (ILV dependency chain)
     // MASKED is a compile-time tag: only the LAST key tile of a sequence with N % 128 != 0 carries the
     // 128 compare+select pairs that push keys past N to -inf (as a run-time predicate the compiler
     // if-converts them into every tile: +2 instructions per score in an issue/MUFU-bound loop)
@@ -234,6 +236,35 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
       const float mb = m_use * scale_log2;
       float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
       uint32_t pk[64];
+      if constexpr (ILV) {
+        // ptxas emits the straightforward loop as three PHASES (128 FFMA, 128 MUFU.EX2, 128 FADD + 64 F2FP): a warp's
+        // MUFU instructions issue 8 cycles apart, so for ~1000 cycles it issues nothing else, and afterwards the MUFU pipe
+        // idles while the warp adds and packs.  The two co-resident CTAs share the pipe processor-style, which keeps their
+        // phases aligned -- the pipe sits idle during BOTH warps' add / pack / load phases (ncu: MUFU pipe 63-65 %).
+        // Here groups of 8 scores are chained through a value-neutral dependency: the offset of group g + 2 is
+        // fma(partial row sum of group g, 0, -mb), so the adds and packs of group g MUST be scheduled before the exp2 of
+        // group g + 2 -- i.e. inside the issue shadow of the MUFU instructions of group g + 1.
+        float nmb_a = -mb, nmb_b = -mb;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) {
+          const float nmb = (g & 1) ? nmb_b : nmb_a;
+          float p[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int j = 8 * g + e;
+            const float x = fmaf(s[j], scale_log2, nmb);
+            p[e] = (POLY && e >= 6) ? ua_exp2_poly(x) : ua_exp2(x);
+          }
+          const float t = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+          if ((g & 3) == 0) rs0 += t; else if ((g & 3) == 1) rs1 += t; else if ((g & 3) == 2) rs2 += t; else rs3 += t;
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) pk[4 * g + (e >> 1)] = pack_bf16x2(p[e], p[e + 1]);
+          // == -mb (t is finite, zero_u is 0 at run time), but it depends on group g's row sum AND on its packed words
+          const uint32_t zbits = ((pk[4 * g] | pk[4 * g + 1]) | (pk[4 * g + 2] | pk[4 * g + 3])) & zero_u;
+          const float dep = fmaf(t, 0.0f, -mb) + __uint_as_float(zbits);
+          if (g & 1) nmb_b = dep; else nmb_a = dep;
+        }
+      } else {
 #pragma unroll
       for (int j = 0; j < 128; j += 2) {
         const float x0 = fmaf(s[j], scale_log2, -mb), x1 = fmaf(s[j + 1], scale_log2, -mb);
@@ -245,6 +276,7 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
         else if (((j >> 1) & 3) == 2) rs2 += p0 + p1;
         else rs3 += p0 + p1;
         pk[j >> 1] = pack_bf16x2(p0, p1);
+      }
       }
       l = l * corr + ((rs0 + rs1) + (rs2 + rs3));
       m = m_use;
@@ -360,14 +392,14 @@ int ua_make_map3d(const void* qkv, int B, int N, int cols, int box_rows, CUtenso
   return 0;
 }
 
-template <int HDP, bool TMA, bool POLY, bool TS>
+template <int HDP, bool TMA, bool POLY, bool TS, bool ILV>
 static int ua_launch(const bf16* qkv, bf16* out, float* lse, int B, int N, int H, int hd, float scale, cudaStream_t s) {
   static bool set = false;
   if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(fa_fwd_umma_kernel<HDP, TMA, POLY, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UaSmem<HDP, TS>::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(fa_fwd_umma_kernel<HDP, TMA, POLY, TS, ILV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UaSmem<HDP, TS>::TOTAL);
     AVJ_CHECK(e == cudaSuccess, "cudaFuncSetAttribute(fa_fwd_umma_kernel) failed: %s", cudaGetErrorString(e));
     // two CTAs per SM need the full 228 KB shared-memory carve-out
-    cudaFuncSetAttribute(fa_fwd_umma_kernel<HDP, TMA, POLY, TS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(fa_fwd_umma_kernel<HDP, TMA, POLY, TS, ILV>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     set = true;
   }
   CUtensorMap map;
@@ -377,7 +409,7 @@ static int ua_launch(const bf16* qkv, bf16* out, float* lse, int B, int N, int H
     if (rc) return rc;
   }
   dim3 grid((N + UA_BM - 1) / UA_BM, H, B);
-  avj_launch_pdl(fa_fwd_umma_kernel<HDP, TMA, POLY, TS>, grid, dim3(UA_THREADS), UaSmem<HDP, TS>::TOTAL, s, map, qkv, out, lse, N, H, hd, scale * 1.4426950408889634f);
+  avj_launch_pdl(fa_fwd_umma_kernel<HDP, TMA, POLY, TS, ILV>, grid, dim3(UA_THREADS), UaSmem<HDP, TS>::TOTAL, s, map, qkv, out, lse, N, H, hd, scale * 1.4426950408889634f, 0u);
   AVJ_LAUNCH_CHECK();
   return 0;
 }
@@ -393,10 +425,13 @@ int avj_attention_fwd_umma(const void* qkv, void* out, float* lse, int B, int N,
   static int ts = -1;          // AVJ_ATTN_TMEM_P=0: P through shared memory instead of tensor memory
   if (ts < 0) { const char* e = getenv("AVJ_ATTN_TMEM_P"); ts = (e && e[0] == '0') ? 0 : 1; }
 #define UA_ARGS (const bf16*)qkv, (bf16*)out, lse, B, N, H, hd, scale, s
+  static int ilv = -1;         // AVJ_ATTN_ILV=0: the plain (phase-ordered) softmax loop of round 1
+  if (ilv < 0) { const char* e = getenv("AVJ_ATTN_ILV"); ilv = (e && e[0] == '0') ? 0 : 1; }
 #define UA_GO(HDP_, TMA_)                                                                             \
   {                                                                                                   \
-    if (ts) return use_poly ? ua_launch<HDP_, TMA_, true, true>(UA_ARGS) : ua_launch<HDP_, TMA_, false, true>(UA_ARGS);   \
-    return use_poly ? ua_launch<HDP_, TMA_, true, false>(UA_ARGS) : ua_launch<HDP_, TMA_, false, false>(UA_ARGS);         \
+    if (ts && ilv) return use_poly ? ua_launch<HDP_, TMA_, true, true, true>(UA_ARGS) : ua_launch<HDP_, TMA_, false, true, true>(UA_ARGS);   \
+    if (ts) return use_poly ? ua_launch<HDP_, TMA_, true, true, false>(UA_ARGS) : ua_launch<HDP_, TMA_, false, true, false>(UA_ARGS);   \
+    return use_poly ? ua_launch<HDP_, TMA_, true, false, false>(UA_ARGS) : ua_launch<HDP_, TMA_, false, false, false>(UA_ARGS);         \
   }
   if (hd <= 32) {
     if (use_tma32 && al) { UA_GO(32, true); }

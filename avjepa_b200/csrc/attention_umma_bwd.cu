@@ -61,7 +61,7 @@ template <int HDP, bool KV> struct UbSmem {
   static constexpr uint32_t R1 = 0, R2 = ROW_TILE, C1 = 2 * ROW_TILE, C2 = C1 + NST * COL_TILE,
                             DS = C2 + NST * COL_TILE, P = DS + UB_PD_TILE,
                             STAT = KV ? P + UB_PD_TILE : P,            // KV pass: [SB][lse2 64 | delta 64] floats
-                            BARS = STAT + (KV ? SB * 512 : 0), TOTAL = BARS + 128;
+                            BARS = STAT + (KV ? SB * 512 : 0), TOTAL = BARS + 192;
 };
 
 // MW = number of math warpgroups (1 or 2).  The score math has no cross-column dependency (row statistics come
@@ -69,7 +69,12 @@ template <int HDP, bool KV> struct UbSmem {
 // twice the warps in flight per scheduler for a latency-bound exp2/FMA loop, half the per-step critical path.
 // TS (HDP == 32 only: 2 x 64 score + 2 x 32 output + 2 x 32 operand columns = 256): P^T / dS^T are written to
 // tensor memory as packed bf16 and consumed as the A operand of the output MMAs from there.
-template <int HDP, bool TMA, bool KV, int MW, bool TS>
+// PP (MW == 2 only): the two math warpgroups are DECOUPLED -- each owns its half of the streamed columns with its own
+// score / operand / output barriers, the MMA thread serves the halves alternately (score MMAs of N = 32, output MMAs of
+// K = 32).  In lockstep (PP = false) both warpgroups wait for the same score MMAs at the same time, so the MUFU pipe
+// idles whenever the CTA waits; decoupled, one half's exp2 math runs under the other half's TMEM loads, operand stores
+// and MMA round trips (ncu, lockstep: 22 % of the math warps' samples sit at the t_full wait, MUFU pipe 47-59 %).
+template <int HDP, bool TMA, bool KV, int MW, bool TS, bool PP>
 __global__ void __launch_bounds__(128 + 128 * MW, 2)
 fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_constant__ CUtensorMap map_qkv64,
                    const __grid_constant__ CUtensorMap map_do, const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
@@ -79,6 +84,7 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
   using TL = UaTile<HDP>;
   constexpr int NST = L::NST;
   static_assert(!TS || HDP == 32, "operands in TMEM need the 256-column budget of HDP = 32");
+  static_assert(!PP || MW == 2, "the decoupled schedule needs two math warpgroups");
   constexpr uint32_t O1_COL = UB_O1_COL, O2_COL = TS ? UB_O1_COL + 32 : UB_O2_COL;
   constexpr uint32_t PT_COL = 192, DST_COL = 224;             // TS: packed bf16 P^T / dS^T, 32 columns each
   extern __shared__ __align__(1024) uint8_t ub_raw[];
@@ -88,13 +94,14 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
   const uint32_t bars = base + L::BARS;
   const uint32_t c_full = bars;             // [NST <= 4]
   const uint32_t c_empty = bars + 32;       // [NST <= 4]
-  const uint32_t t_full = bars + 64;
-  const uint32_t t_free = bars + 72;
-  const uint32_t p_full = bars + 80;
-  const uint32_t o_done = bars + 88;
-  const uint32_t tmem_slot = bars + 96;
-  const uint32_t r_ready = bars + 104;      // count 32: pad columns of the stationary tiles zeroed (TMA, hd < HDP)
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(ub_raw + L::BARS + 96);
+  const uint32_t t_full = bars + 64;        // [2] (PP: one per column half; else only [0])
+  const uint32_t t_free = bars + 80;        // [2]
+  const uint32_t p_full = bars + 96;        // [2]
+  const uint32_t o_done = bars + 112;       // [2]
+  const uint32_t tmem_slot = bars + 128;
+  const uint32_t r_ready = bars + 136;      // count 32: pad columns of the stationary tiles zeroed (TMA, hd < HDP)
+  const uint32_t all_done = bars + 144;     // count 1: every output MMA of the CTA has retired
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(ub_raw + L::BARS + 128);
 
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -118,7 +125,11 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
     if (base & 1023u) __trap();
     ua_mbar_init(r_ready, 32);
     for (int i = 0; i < NST; ++i) { ua_mbar_init(c_full + 8 * i, TMA ? 1 : UB_LOADERS); ua_mbar_init(c_empty + 8 * i, 1); }
-    ua_mbar_init(t_full, 1); ua_mbar_init(t_free, 128 * MW); ua_mbar_init(p_full, 128 * MW); ua_mbar_init(o_done, 1);
+    constexpr uint32_t NB = PP ? 2 : 1, CNT = PP ? 128 : 128 * MW;
+    for (uint32_t i = 0; i < NB; ++i) {
+      ua_mbar_init(t_full + 8 * i, 1); ua_mbar_init(t_free + 8 * i, CNT); ua_mbar_init(p_full + 8 * i, CNT); ua_mbar_init(o_done + 8 * i, 1);
+    }
+    ua_mbar_init(all_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -206,46 +217,86 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
         for (int k = 0; k < HDP / 16; ++k) ua_mma(tmem + UB_T2_COL, r2d + 2 * k, c2d + 2 * k, idesc_t, k > 0 ? 1u : 0u);
         ua_commit(t_full);
       };
-      ua_mbar_wait(c_full, 0);
-      if (zero_pad) ua_mbar_wait(r_ready, 0);
-      ua_fence_after();
-      issue_scores(0);
-      for (int t = 0; t < T; ++t) {
-        if (t + 1 < T) {
-          ua_mbar_wait(c_full + 8 * ((t + 1) % NST), ((t + 1) / NST) & 1);
-          ua_mbar_wait(t_free, t & 1);                       // both score tiles of step t are in registers
-          ua_fence_after();
-          issue_scores(t + 1);
-        }
-        ua_mbar_wait(p_full, t & 1);
-        ua_fence_after();
+      // one column half (32 streamed rows) of both score products; PP only
+      const uint32_t idesc_h = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(UB_BM >> 4) << 24);
+      auto issue_scores_half = [&](int t, int hf) {
+        const uint32_t off = (uint32_t)hf * 32u * TL::PITCH;                 // 32 streamed rows further into the tile
+        const uint64_t c1d = TL::kmajor(sC1 + (t % NST) * L::COL_TILE + off);
+        const uint64_t c2d = TL::kmajor(sC2 + (t % NST) * L::COL_TILE + off);
+#pragma unroll
+        for (int k = 0; k < HDP / 16; ++k) ua_mma(tmem + 32 * hf, r1d + 2 * k, c1d + 2 * k, idesc_h, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < HDP / 16; ++k) ua_mma(tmem + UB_T2_COL + 32 * hf, r2d + 2 * k, c2d + 2 * k, idesc_h, k > 0 ? 1u : 0u);
+        ua_commit(t_full + 8 * hf);
+      };
+      // output MMAs of step t over the K steps [k0, k1) of the 64 streamed columns
+      auto issue_outputs = [&](int t, int k0, int k1) {
         const uint32_t c1 = sC1 + (t % NST) * L::COL_TILE, c2 = sC2 + (t % NST) * L::COL_TILE;
-        const uint32_t accum0 = t > 0 ? 1u : 0u;
         const uint64_t dsd = ua_desc(sDS, 1, 64);
         const uint64_t c1m = TL::mnmajor(c1);                // MN-major view: 16 streamed rows per K step
         if (KV) {
           const uint64_t pd = ua_desc(sP, 1, 64);
           const uint64_t c2m = TL::mnmajor(c2);
 #pragma unroll
-          for (int k = 0; k < UB_BN / 16; ++k) {                                               // dV += P^T dO
-            if (TS) ua_mma_ts(tmem + O1_COL, tmem + PT_COL + 8 * k, c2m + TL::MN_KADV * k, idesc_o, (accum0 | (k > 0)) ? 1u : 0u);
-            else    ua_mma(tmem + O1_COL, pd + 2 * k, c2m + TL::MN_KADV * k, idesc_o, (accum0 | (k > 0)) ? 1u : 0u);
+          for (int k = k0; k < k1; ++k) {                                                      // dV += P^T dO
+            const uint32_t acc = (t > 0 || k > 0) ? 1u : 0u;
+            if (TS) ua_mma_ts(tmem + O1_COL, tmem + PT_COL + 8 * k, c2m + TL::MN_KADV * k, idesc_o, acc);
+            else    ua_mma(tmem + O1_COL, pd + 2 * k, c2m + TL::MN_KADV * k, idesc_o, acc);
           }
 #pragma unroll
-          for (int k = 0; k < UB_BN / 16; ++k) {                                               // dK += dS^T Q
-            if (TS) ua_mma_ts(tmem + O2_COL, tmem + DST_COL + 8 * k, c1m + TL::MN_KADV * k, idesc_o, (accum0 | (k > 0)) ? 1u : 0u);
-            else    ua_mma(tmem + O2_COL, dsd + 2 * k, c1m + TL::MN_KADV * k, idesc_o, (accum0 | (k > 0)) ? 1u : 0u);
+          for (int k = k0; k < k1; ++k) {                                                      // dK += dS^T Q
+            const uint32_t acc = (t > 0 || k > 0) ? 1u : 0u;
+            if (TS) ua_mma_ts(tmem + O2_COL, tmem + DST_COL + 8 * k, c1m + TL::MN_KADV * k, idesc_o, acc);
+            else    ua_mma(tmem + O2_COL, dsd + 2 * k, c1m + TL::MN_KADV * k, idesc_o, acc);
           }
         } else {
 #pragma unroll
-          for (int k = 0; k < UB_BN / 16; ++k) {                                               // dQ += dS K
-            if (TS) ua_mma_ts(tmem + O1_COL, tmem + DST_COL + 8 * k, c1m + TL::MN_KADV * k, idesc_o, (accum0 | (k > 0)) ? 1u : 0u);
-            else    ua_mma(tmem + O1_COL, dsd + 2 * k, c1m + TL::MN_KADV * k, idesc_o, (accum0 | (k > 0)) ? 1u : 0u);
+          for (int k = k0; k < k1; ++k) {                                                      // dQ += dS K
+            const uint32_t acc = (t > 0 || k > 0) ? 1u : 0u;
+            if (TS) ua_mma_ts(tmem + O1_COL, tmem + DST_COL + 8 * k, c1m + TL::MN_KADV * k, idesc_o, acc);
+            else    ua_mma(tmem + O1_COL, dsd + 2 * k, c1m + TL::MN_KADV * k, idesc_o, acc);
           }
         }
-        ua_commit(o_done);
-        ua_commit(c_empty + 8 * (t % NST));
+      };
+      ua_mbar_wait(c_full, 0);
+      if (zero_pad) ua_mbar_wait(r_ready, 0);
+      ua_fence_after();
+      if constexpr (PP) {
+        issue_scores_half(0, 0);
+        issue_scores_half(0, 1);
+        for (int t = 0; t < T; ++t) {
+          if (t + 1 < T) ua_mbar_wait(c_full + 8 * ((t + 1) % NST), ((t + 1) / NST) & 1);
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            if (t + 1 < T) {
+              ua_mbar_wait(t_free + 8 * hf, t & 1);            // this half's scores of step t are in registers
+              ua_fence_after();
+              issue_scores_half(t + 1, hf);
+            }
+            ua_mbar_wait(p_full + 8 * hf, t & 1);
+            ua_fence_after();
+            issue_outputs(t, 2 * hf, 2 * hf + 2);
+            ua_commit(o_done + 8 * hf);
+          }
+          ua_commit(c_empty + 8 * (t % NST));
+        }
+      } else {
+        issue_scores(0);
+        for (int t = 0; t < T; ++t) {
+          if (t + 1 < T) {
+            ua_mbar_wait(c_full + 8 * ((t + 1) % NST), ((t + 1) / NST) & 1);
+            ua_mbar_wait(t_free, t & 1);                       // both score tiles of step t are in registers
+            ua_fence_after();
+            issue_scores(t + 1);
+          }
+          ua_mbar_wait(p_full, t & 1);
+          ua_fence_after();
+          issue_outputs(t, 0, UB_BN / 16);
+          ua_commit(o_done);
+          ua_commit(c_empty + 8 * (t % NST));
+        }
       }
+      ua_commit(all_done);
     }
   }
   } else {
@@ -263,29 +314,42 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
     if (!KV && ri < N) { my_l2 = lse_bh[ri]; my_dl = delta_bh[ri]; }
     float* stat = reinterpret_cast<float*>(ub_raw + L::STAT);
     float my_stat = 0.f;
-    if (KV && wg == 0) my_stat = __ldg((row < 64 ? lse_bh : delta_bh - 64) + row);   // tile 0 (rows are padded to n_pad with zeros)
+    // PP: barriers of my column half; statistics staged per warpgroup (threads 0-31: lse2 of my 32 columns, 32-63: delta)
+    const uint32_t bo = PP ? 8u * (uint32_t)wg : 0u;
+    const float* pp_src = (row < 32 ? lse_bh + col0 + row : delta_bh + col0 + (row - 32));
+    if (KV && !PP && wg == 0) my_stat = __ldg((row < 64 ? lse_bh : delta_bh - 64) + row);   // tile 0 (rows are padded to n_pad with zeros)
+    if (KV && PP && row < 64) my_stat = __ldg(pp_src);
     for (int t = 0; t < T; ++t) {
-      ua_mbar_wait(t_full, t & 1);
+      ua_mbar_wait(t_full + bo, t & 1);
       ua_fence_after();
       float s[CW], dp[CW];
 #pragma unroll
       for (int c = 0; c < CW; c += 32) { ua_ld32(t_1 + col0 + c, s + c); ua_ld32(t_1 + UB_T2_COL + col0 + c, dp + c); }
       ua_ld_wait();
       ua_fence_before();
-      ua_mbar_arrive(t_free);
+      ua_mbar_arrive(t_free + bo);
       uint32_t pk_p[KV ? CW / 2 : 1], pk_d[CW / 2];
       // per-column statistics of this query tile: thread i publishes ONE value (i < 64: lse2 of column i,
       // else delta of column i - 64) that it loaded a whole step earlier, so no thread ever waits on global
       // memory; everybody then reads the 2 x 256 bytes as shared-memory broadcasts
-      if constexpr (KV) {
+      if constexpr (KV && PP) {
+        float* sb = stat + (t % L::SB) * 128 + wg * 64;       // [lse2 of my 32 columns | delta of my 32 columns]
+        auto wg_sync = [&] {                                   // named barrier of my warpgroup (immediate ids: a register id reserves all 16)
+          if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+        };
+        if (L::SB == 1) wg_sync();                             // my warpgroup's readers of the previous tile are done
+        if (row < 64) sb[row] = my_stat;
+        wg_sync();
+        if (row < 64 && t + 1 < T) my_stat = __ldg(pp_src + (t + 1) * UB_BN);
+      } else if constexpr (KV) {
         float* sb = stat + (t % L::SB) * 128;
         if (L::SB == 1) asm volatile("bar.sync 1, %0;" ::"n"(128 * MW) : "memory");   // previous tile's readers are done
         if (wg == 0) sb[row] = my_stat;
         asm volatile("bar.sync 1, %0;" ::"n"(128 * MW) : "memory");
         if (wg == 0 && t + 1 < T) my_stat = __ldg((row < 64 ? lse_bh : delta_bh - 64) + (t + 1) * UB_BN + row);
       }
-      const float* st_l2 = stat + (KV ? (t % L::SB) * 128 : 0) + col0;
-      const float* st_dl = st_l2 + 64;
+      const float* st_l2 = stat + (KV ? (t % L::SB) * 128 : 0) + (PP ? wg * 64 : col0);
+      const float* st_dl = st_l2 + (PP ? 32 : 64);
 #pragma unroll
       for (int j = 0; j < CW; j += 4) {
         float l2[4], dl[4];
@@ -307,7 +371,7 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
         if constexpr (KV) { pk_p[j >> 1] = pack_bf16x2(p[0], p[1]); pk_p[(j >> 1) + 1] = pack_bf16x2(p[2], p[3]); }
         pk_d[j >> 1] = pack_bf16x2(ds[0], ds[1]); pk_d[(j >> 1) + 1] = pack_bf16x2(ds[2], ds[3]);
       }
-      if (t > 0) ua_mbar_wait(o_done, (t - 1) & 1);           // output MMAs of step t-1 done: P / dS smem is ours
+      if (t > 0) ua_mbar_wait(o_done + bo, (t - 1) & 1);      // output MMAs of step t-1 done: P / dS smem is ours
       ua_fence_after();
       if constexpr (TS) {
         ua_st_regs<CW / 2>(t_1 + DST_COL + col0 / 2, pk_d);
@@ -326,9 +390,9 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
         ua_fence_async_smem();
       }
       ua_fence_before();
-      ua_mbar_arrive(p_full);
+      ua_mbar_arrive(p_full + bo);
     }
-    ua_mbar_wait(o_done, (T - 1) & 1);
+    ua_mbar_wait(all_done, 0);
     ua_fence_after();
     // dqkv row layout [3][H][hd]: slot 0 = dQ, 1 = dK, 2 = dV
     bf16* drow = dqkv + ((int64_t)b * N + ri) * rs + (int64_t)h * hd;
@@ -376,26 +440,26 @@ bool avj_attention_umma_bwd_supported(int dtype, int hd) {
   return dtype == AVJ_BF16 && hd % 8 == 0 && hd >= 8 && hd <= 64;
 }
 
-template <int HDP, bool TMA, bool KV, int MW, bool TS>
+template <int HDP, bool TMA, bool KV, int MW, bool TS, bool PP>
 static int ub_launch(const CUtensorMap& m128, const CUtensorMap& m64, const CUtensorMap& mdo, const bf16* qkv, const bf16* dout,
                      const float* lse2, const float* delta, bf16* dqkv, int B, int N, int n_pad, int H, int hd, float scale,
                      cudaStream_t s) {
   static bool set = false;
   const int smem = (int)UbSmem<HDP, KV>::TOTAL;
   if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(fa_bwd_umma_kernel<HDP, TMA, KV, MW, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(fa_bwd_umma_kernel<HDP, TMA, KV, MW, TS, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     AVJ_CHECK(e == cudaSuccess, "cudaFuncSetAttribute(fa_bwd_umma_kernel) failed: %s", cudaGetErrorString(e));
-    cudaFuncSetAttribute(fa_bwd_umma_kernel<HDP, TMA, KV, MW, TS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(fa_bwd_umma_kernel<HDP, TMA, KV, MW, TS, PP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     set = true;
   }
   dim3 grid((N + UB_BM - 1) / UB_BM, H, B);
-  avj_launch_pdl(fa_bwd_umma_kernel<HDP, TMA, KV, MW, TS>, grid, dim3(128 + 128 * MW), (size_t)smem, s, m128, m64, mdo, qkv, dout, lse2, delta, dqkv, N, n_pad,
+  avj_launch_pdl(fa_bwd_umma_kernel<HDP, TMA, KV, MW, TS, PP>, grid, dim3(128 + 128 * MW), (size_t)smem, s, m128, m64, mdo, qkv, dout, lse2, delta, dqkv, N, n_pad,
                  H, hd, scale, scale * 1.4426950408889634f);
   AVJ_LAUNCH_CHECK();
   return 0;
 }
 
-template <int HDP, bool TMA, int MW, bool TS>
+template <int HDP, bool TMA, int MW, bool TS, bool PP>
 static int ub_both(const bf16* qkv, const bf16* dout, const float* lse2, const float* delta, bf16* dqkv,
                    int B, int N, int n_pad, int H, int hd, float scale, cudaStream_t s) {
   CUtensorMap m128, m64, mdo64, mdo128;
@@ -407,9 +471,9 @@ static int ub_both(const bf16* qkv, const bf16* dout, const float* lse2, const f
     if ((rc = ua_make_map3d(dout, B, N, H * hd, 64, &mdo64, HDP))) return rc;
     if ((rc = ua_make_map3d(dout, B, N, H * hd, 128, &mdo128, HDP))) return rc;
   }
-  int rc = ub_launch<HDP, TMA, true, MW, TS>(m128, m64, mdo64, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
+  int rc = ub_launch<HDP, TMA, true, MW, TS, PP>(m128, m64, mdo64, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
   if (rc) return rc;
-  return ub_launch<HDP, TMA, false, MW, TS>(m128, m64, mdo128, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
+  return ub_launch<HDP, TMA, false, MW, TS, PP>(m128, m64, mdo128, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
 }
 
 int avj_attention_bwd_umma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* ws,
@@ -430,7 +494,13 @@ int avj_attention_bwd_umma(const void* qkv, const void* out, const void* dout, c
   static int ts = -1;          // AVJ_ATTN_TMEM_P=0: P^T / dS^T through shared memory for head_dim <= 32 as well
   if (ts < 0) { const char* e = getenv("AVJ_ATTN_TMEM_P"); ts = (e && e[0] == '0') ? 0 : 1; }
 #define UB_ARGS (const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, B, N, n_pad, H, hd, scale, s
-#define UB_GO(HDP_, TMA_, TS_) return mw == 2 ? ub_both<HDP_, TMA_, 2, TS_>(UB_ARGS) : ub_both<HDP_, TMA_, 1, TS_>(UB_ARGS)
+  static int pp = -1;          // AVJ_ATTN_BWD_PP=1: decoupled math warpgroups (measured SLOWER than lockstep: 0.677 vs 0.550 ms predictor, 1.59 vs 1.27 ms target)
+  if (pp < 0) { const char* e = getenv("AVJ_ATTN_BWD_PP"); pp = (e && e[0] == '1') ? 1 : 0; }
+#define UB_GO(HDP_, TMA_, TS_)                                                                             \
+  {                                                                                                        \
+    if (mw == 2 && pp) return ub_both<HDP_, TMA_, 2, TS_, true>(UB_ARGS);                                  \
+    return mw == 2 ? ub_both<HDP_, TMA_, 2, TS_, false>(UB_ARGS) : ub_both<HDP_, TMA_, 1, TS_, false>(UB_ARGS); \
+  }
   if (hd <= 32) {
     if (use_tma32 && aligned) { if (ts) { UB_GO(32, true, true); } UB_GO(32, true, false); }
     if (ts) { UB_GO(32, false, true); }

@@ -241,12 +241,12 @@ colsum_partial_kernel(const T* __restrict__ in, int ld, avj_rowmap map, float* _
   if (c0 < D) {
     const int r_beg = blockIdx.y * chunk, r_end = min(rows, r_beg + chunk);
     int r = r_beg + threadIdx.y;
-    for (; r + 24 < r_end; r += 32) {
-      float v[4][8];
+    for (; r + 56 < r_end; r += 64) {                  // eight independent 16-byte loads in flight per thread
+      float v[8][8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) load8<T>(in + map_row(map, r + 8 * u) * ld + c0, v[u]);
+      for (int u = 0; u < 8; ++u) load8<T>(in + map_row(map, r + 8 * u) * ld + c0, v[u]);
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 8; ++u)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] += v[u][j];
     }
@@ -288,7 +288,7 @@ extern "C" int avj_colsum(const void* in, int in_dtype, int ld, avj_rowmap map, 
   if (rows == 0 || D == 0) return 0;
   AvjProfScope prof(AVJ_FAM_COLSUM, (double)rows * D * (in_dtype == AVJ_BF16 ? 2 : 4), stream, rows, D);
   const int gx = (D + 255) / 256;
-  int ny = (4 * avj_num_sms() + gx - 1) / gx;                 // ~4 CTAs per SM
+  int ny = (6 * avj_num_sms() + gx - 1) / gx;                 // ~6 CTAs per SM
   if (ny > COLSUM_MAX_Y) ny = COLSUM_MAX_Y;
   if (ny > (rows + 63) / 64) ny = (rows + 63) / 64;           // at least 64 rows per CTA
   if (ny < 1) ny = 1;
@@ -322,12 +322,12 @@ colsum2_partial_kernel(const T* __restrict__ in1, int ld1, int D1, const T* __re
   if (c0 < D) {
     const int r_beg = blockIdx.y * chunk, r_end = min(rows, r_beg + chunk);
     int r = r_beg + threadIdx.y;
-    for (; r + 24 < r_end; r += 32) {
-      float v[4][8];
+    for (; r + 56 < r_end; r += 64) {                  // eight independent 16-byte loads in flight per thread
+      float v[8][8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) load8<T>(in + (int64_t)(r + 8 * u) * ld + c0, v[u]);
+      for (int u = 0; u < 8; ++u) load8<T>(in + (int64_t)(r + 8 * u) * ld + c0, v[u]);
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 8; ++u)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] += v[u][j];
     }
@@ -372,7 +372,7 @@ extern "C" int avj_colsum2(const void* in1, int ld1, int D1, float* out1, const 
   if (rows == 0) return 0;
   AvjProfScope prof(AVJ_FAM_COLSUM, (double)rows * (D1 + D2) * (in_dtype == AVJ_BF16 ? 2 : 4), stream, rows, D1, D2);
   const int gx1 = (D1 + 255) / 256, gx = gx1 + (D2 + 255) / 256;
-  int ny = (4 * avj_num_sms() + gx - 1) / gx;
+  int ny = (6 * avj_num_sms() + gx - 1) / gx;
   if (ny > COLSUM_MAX_Y) ny = COLSUM_MAX_Y;
   if (ny > (rows + 63) / 64) ny = (rows + 63) / 64;
   if (ny < 1) ny = 1;

@@ -862,11 +862,27 @@ int avj_gemm_umma(int layout, const void* A, const void* B, void* C, int M, int 
   const bool pure_accumulate = ep.accumulate && ep.out_dtype == AVJ_F32 && !ep.bias && !ep.residual && !ep.pos &&
                                !ep.act && !ep.dact_aux;
   if (pure_accumulate && tiles < 2 * workers && p.k_blocks >= 8) {
-    int want = (2 * workers + tiles - 1) / tiles;
+    // split-K factor from a wave model: a unit costs its k-blocks plus a fixed epilogue (~6 k-block times for a
+    // 256 x 256 fp32 read-modify-write), the launch takes ceil(units / workers) waves of the slowest unit.  The old
+    // rule (2 waves' worth of units) left partial last waves: 18 tiles x 9 splits = 162 units on 74 CTA pairs = 3 waves
+    // at 73 % occupancy; the model picks 4 splits = 72 units = 1 full wave.
+    static const uint32_t old_rule = env_u32("AVJ_GEMM_SPLITK_OLD", 0);
     int max_split = p.k_blocks / 4;
-    if (want > max_split) want = max_split;
-    if (want < 1) want = 1;
-    p.split_k = want;
+    if (max_split > 32) max_split = 32;
+    if (old_rule) {
+      int want = (2 * workers + tiles - 1) / tiles;
+      if (want > p.k_blocks / 4) want = p.k_blocks / 4;
+      p.split_k = want < 1 ? 1 : want;
+    } else {
+      double best = -1.0;
+      for (int sp = 1; sp <= max_split; ++sp) {
+        const int kbs = (p.k_blocks + sp - 1) / sp;
+        const int eff = (p.k_blocks + kbs - 1) / kbs;
+        const int waves = (tiles * eff + workers - 1) / workers;
+        const double t = waves * (kbs + 6.0);
+        if (best < 0.0 || t < best * 0.98) { best = t; p.split_k = eff; }
+      }
+    }
   }
   p.kb_per_split = (p.k_blocks + p.split_k - 1) / p.split_k;
   p.split_k = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;   // drop empty splits

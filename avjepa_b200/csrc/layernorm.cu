@@ -215,24 +215,32 @@ layernorm_bwd_kernel(const TDY* __restrict__ dy, const float* __restrict__ x, co
   }
 }
 
-// cross-block reduction of the [nblocks][2D] partials: 32 columns x 8 row groups per block
-__global__ void __launch_bounds__(256)
+// cross-block reduction of the [nblocks][3D] partials: 32 columns x 32 row groups per block, four independent loads in
+// flight per thread (the partials sit in L2: the reduction is latency-, not bandwidth-bound)
+__global__ void __launch_bounds__(1024)
 layernorm_bwd_final_kernel(const float* __restrict__ ws, int nblocks, int D,
                            float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcolsum) {
-  __shared__ float red[8][33];
+  __shared__ float red[32][33];
   pdl_trigger();
   pdl_wait();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
-  float t = 0.f;
-  if (c < 3 * D)
-    for (int b = ty; b < nblocks; b += 8) t += ws[(size_t)b * 3 * D + c];
-  red[ty][tx] = t;
+  float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+  if (c < 3 * D) {
+    const size_t st = (size_t)3 * D;
+    int b = ty;
+    for (; b + 96 < nblocks; b += 128) {
+      t0 += ws[(size_t)b * st + c]; t1 += ws[(size_t)(b + 32) * st + c];
+      t2 += ws[(size_t)(b + 64) * st + c]; t3 += ws[(size_t)(b + 96) * st + c];
+    }
+    for (; b < nblocks; b += 32) t0 += ws[(size_t)b * st + c];
+  }
+  red[ty][tx] = (t0 + t1) + (t2 + t3);
   __syncthreads();
   if (ty == 0 && c < 3 * D) {
     float v = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v += red[j][tx];
+    for (int j = 0; j < 32; ++j) v += red[j][tx];
     if (c < D) { if (dgamma) dgamma[c] += v; }
     else if (c < 2 * D) { if (dbeta) dbeta[c - D] += v; }
     else { if (dcolsum) dcolsum[c - 2 * D] += v; }
@@ -264,7 +272,7 @@ static int launch_ln_bwd(const TDY* dy, const float* x, const float* gamma, cons
 #undef LNB_CASE
   AVJ_LAUNCH_CHECK();
   if (want || want_cs) {
-    avj_launch_pdl(layernorm_bwd_final_kernel, dim3((3 * D + 31) / 32), dim3(256), 0, s, ws, grid, D, dgamma, dbeta, dcolsum);
+    avj_launch_pdl(layernorm_bwd_final_kernel, dim3((3 * D + 31) / 32), dim3(1024), 0, s, ws, grid, D, dgamma, dbeta, dcolsum);
     AVJ_LAUNCH_CHECK();
   }
   return 0;

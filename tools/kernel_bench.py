@@ -157,6 +157,30 @@ def bench_gather(B, N, K, D):
                           frac=round(gbs / PEAKS['hbm_gbs'], 3))), flush=True)
 
 
+def bench_loss(rows, D):
+    z = torch.randn((rows, D), device=DEV)
+    h = torch.randn((rows, D), device=DEV)
+    dz = torch.empty_like(z)
+    out = torch.zeros(1, device=DEV)
+    ws = torch.empty(int(_cabi.load().avj_loss_ws_floats(z.numel())), device=DEV)
+    ms = timeit(lambda: _cabi.call('avj_loss_fwd_bwd', z.data_ptr(), h.data_ptr(), dz.data_ptr(), out.data_ptr(), z.numel(), 2, 1.0, 0, 0.0,
+                                   1.0, ws.data_ptr(), engine.stream()))
+    gbs = rows * D * 12 / (ms * 1e-3) / 1e9
+    print(json.dumps(dict(kernel='loss_fwd_bwd', rows=rows, D=D, ms=round(ms, 4), gbs=round(gbs, 1), frac=round(gbs / PEAKS['hbm_gbs'], 3))), flush=True)
+
+
+def bench_colsum2(rows, D1, D2):
+    a = torch.randn((rows, D1), device=DEV).bfloat16()
+    b = torch.randn((rows, D2), device=DEV).bfloat16()
+    o1 = torch.zeros(D1, device=DEV)
+    o2 = torch.zeros(D2, device=DEV)
+    ws = torch.empty(int(_cabi.load().avj_colsum_ws_floats(rows, D1 + D2)), device=DEV)
+    ms = timeit(lambda: _cabi.call('avj_colsum2', a.data_ptr(), D1, D1, o1.data_ptr(), b.data_ptr(), D2, D2, o2.data_ptr(), BF16, rows,
+                                   ws.data_ptr(), engine.stream()))
+    gbs = rows * (D1 + D2) * 2 / (ms * 1e-3) / 1e9
+    print(json.dumps(dict(kernel='colsum2', rows=rows, D1=D1, D2=D2, ms=round(ms, 4), gbs=round(gbs, 1), frac=round(gbs / PEAKS['hbm_gbs'], 3))), flush=True)
+
+
 if __name__ == '__main__':
     which = sys.argv[1] if len(sys.argv) > 1 else 'all'
     R_T, R_C, R_P = 24 * 1664, 24 * 384, 24 * 1216      # target / context / predictor rows at ViT-L, B=24
@@ -182,6 +206,10 @@ if __name__ == '__main__':
         bench_attn(24, 1216, 16, 24, 'predictor')
     if which in ('all', 'misc'):
         bench_ln(R_T, 1024)
-        bench_ln(R_P, 384)
+        bench_ln(24 * 537, 1024)
+        bench_ln(24 * 2450, 384)
+        bench_colsum2(24 * 537, 3072, 4096)
+        bench_colsum2(24 * 2450, 1152, 1536)
         bench_adamw(300_000_000)
         bench_gather(24, 1568, 800, 1024)
+        bench_loss(24 * 1144, 1024)

@@ -27,6 +27,12 @@ CASES = {
     'attn_target': lambda: kb.bench_attn(24, 1664, 16, 64, 'target enc'),
     'attn_pred': lambda: kb.bench_attn(24, 1216, 16, 24, 'predictor'),
     'ln': lambda: kb.bench_ln(R_T, 1024),
+    'ln_ctx': lambda: kb.bench_ln(24 * 537, 1024),
+    'ln_pred': lambda: kb.bench_ln(24 * 2450, 384),
+    'colsum': lambda: kb.bench_colsum2(24 * 537, 3072, 4096),
+    'adamw': lambda: kb.bench_adamw(300_000_000),
+    'gather': lambda: kb.bench_gather(24, 1568, 800, 1024),
+    'loss': lambda: kb.bench_loss(24 * 1144, 1024),
 }
 
 if __name__ == '__main__':

@@ -74,17 +74,26 @@ template <int HDP, bool KV> struct UbSmem {
 // K = 32).  In lockstep (PP = false) both warpgroups wait for the same score MMAs at the same time, so the MUFU pipe
 // idles whenever the CTA waits; decoupled, one half's exp2 math runs under the other half's TMEM loads, operand stores
 // and MMA round trips (ncu, lockstep: 22 % of the math warps' samples sit at the t_full wait, MUFU pipe 47-59 %).
-template <int HDP, bool TMA, bool KV, int MW, bool TS, bool PP>
+// SP (single pass; KV pass only, HDP == 32, TMA, TS, MW == 2): the KV-owner CTA ALSO produces dQ, so the Q pass -- and its
+// second evaluation of every exp2 -- disappears.  Per step dQ_tile[64 q, hd] = dS[64 q, 128 keys] K[128 keys, hd] is one more
+// group of tcgen05.mma (M = 64; A = the dS^T tile in shared memory read MN-major, B = the stationary K tile read MN-major),
+// its fp32 result leaves TMEM through a 64 x hd staging tile and ONE TMA reduce-add (cp.reduce.async.bulk.tensor .add)
+// into an fp32 dQ accumulator [B, N, H, hd]; dS^T therefore lives in shared memory (it feeds dK K-major and dQ MN-major),
+// P^T stays in tensor memory.  TMEM: S^T 64 | dP^T 64 | dV 32 | dK 32 | P^T 32 | dQ 32 = 256 columns.
+template <int HDP, bool TMA, bool KV, int MW, bool TS, bool PP, bool SP>
 __global__ void __launch_bounds__(128 + 128 * MW, 2)
 fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_constant__ CUtensorMap map_qkv64,
-                   const __grid_constant__ CUtensorMap map_do, const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+                   const __grid_constant__ CUtensorMap map_do, const __grid_constant__ CUtensorMap map_dq,
+                   const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                    const float* __restrict__ lse2, const float* __restrict__ delta, bf16* __restrict__ dqkv,
-                   int N, int n_pad, int H, int hd, float scale, float scale_log2) {
+                   int N, int n_pad, int H, int hd, float scale, float scale_log2, int dbg) {
   using L = UbSmem<HDP, KV>;
   using TL = UaTile<HDP>;
   constexpr int NST = L::NST;
   static_assert(!TS || HDP == 32, "operands in TMEM need the 256-column budget of HDP = 32");
   static_assert(!PP || MW == 2, "the decoupled schedule needs two math warpgroups");
+  static_assert(!SP || (KV && HDP == 32 && TMA && TS && MW == 2 && !PP), "single pass: KV pass, HDP 32, TMA, P^T in TMEM, two lockstep warpgroups");
+  constexpr uint32_t DQ_COL = 224;                            // SP: dQ tile (M = 64: rows 16j + i sit in lane 32j + i)
   constexpr uint32_t O1_COL = UB_O1_COL, O2_COL = TS ? UB_O1_COL + 32 : UB_O2_COL;
   constexpr uint32_t PT_COL = 192, DST_COL = 224;             // TS: packed bf16 P^T / dS^T, 32 columns each
   extern __shared__ __align__(1024) uint8_t ub_raw[];
@@ -237,6 +246,23 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
         if (KV) {
           const uint64_t pd = ua_desc(sP, 1, 64);
           const uint64_t c2m = TL::mnmajor(c2);
+          if constexpr (SP) {
+            // three INDEPENDENT accumulation chains (dV: 4 MMAs, dK: 4, dQ tile: 8).  Small dependent MMAs are latency-, not
+            // throughput-bound (ncu: tensor pipe 21 % busy while the math warps wait for these 16 MMAs), so the chains are
+            // issued round-robin instead of one after the other.
+            const uint32_t idesc_q = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(HDP >> 3) << 17) |
+                                     ((uint32_t)(64 >> 4) << 24);
+            const uint64_t dsm = ua_desc(sDS, 512, 64);      // MN-major view of dS^T: 64 queries contiguous, 16 keys per K step
+            const uint64_t r1m = TL::mnmajor(sR1);           // K tile: 16 keys per K step, hd contiguous
+#pragma unroll
+            for (int k = 0; k < UB_BN / 16; ++k) {
+              const uint32_t acc = (t > 0 || k > 0) ? 1u : 0u;
+              ua_mma(tmem + DQ_COL, dsm + 128 * (2 * k), r1m + TL::MN_KADV * (2 * k), idesc_q, k > 0 ? 1u : 0u);
+              ua_mma_ts(tmem + O1_COL, tmem + PT_COL + 8 * k, c2m + TL::MN_KADV * k, idesc_o, acc);           // dV += P^T dO
+              ua_mma(tmem + DQ_COL, dsm + 128 * (2 * k + 1), r1m + TL::MN_KADV * (2 * k + 1), idesc_q, 1u);
+              ua_mma(tmem + O2_COL, dsd + 2 * k, c1m + TL::MN_KADV * k, idesc_o, acc);                        // dK += dS^T Q
+            }
+          } else {
 #pragma unroll
           for (int k = k0; k < k1; ++k) {                                                      // dV += P^T dO
             const uint32_t acc = (t > 0 || k > 0) ? 1u : 0u;
@@ -248,6 +274,7 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
             const uint32_t acc = (t > 0 || k > 0) ? 1u : 0u;
             if (TS) ua_mma_ts(tmem + O2_COL, tmem + DST_COL + 8 * k, c1m + TL::MN_KADV * k, idesc_o, acc);
             else    ua_mma(tmem + O2_COL, dsd + 2 * k, c1m + TL::MN_KADV * k, idesc_o, acc);
+          }
           }
         } else {
 #pragma unroll
@@ -319,6 +346,34 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
     const float* pp_src = (row < 32 ? lse_bh + col0 + row : delta_bh + col0 + (row - 32));
     if (KV && !PP && wg == 0) my_stat = __ldg((row < 64 ? lse_bh : delta_bh - 64) + row);   // tile 0 (rows are padded to n_pad with zeros)
     if (KV && PP && row < 64) my_stat = __ldg(pp_src);
+    // SP: dQ tile of step tq (fp32 [64 q, hd], M = 64 accumulator: row 16j + i in TMEM lane 32j + i) -> dense staging tile in
+    // the (otherwise unused) sP region -> one TMA reduce-add into dq_acc[b, tq*64 .., h, :].  Warp (q, wg) moves columns
+    // [16 wg, 16 wg + 16) of rows [16 q, 16 q + 16).  The staging tile is known to be free: the issuing thread waited for the
+    // previous reduce to have READ it before this step's statistics barrier (bar.sync 1), which every math thread has passed.
+    const bool dq_issuer = (threadIdx.x == 128);
+    auto flush_dq = [&](int tq) {
+      uint32_t v[16];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+          : "r"(t_1 + DQ_COL + 16 * wg) : "memory");
+      ua_ld_wait();
+      if (lane < 16) {
+        const uint32_t dst = sP + (uint32_t)((16 * q + lane) * hd + 16 * wg) * 4u;
+#pragma unroll
+        for (int c = 0; c < 16; c += 4)
+          if (16 * wg + c < hd)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 4 * c), "r"(v[c]), "r"(v[c + 1]), "r"(v[c + 2]), "r"(v[c + 3]) : "memory");
+      }
+      ua_fence_async_smem();
+      asm volatile("bar.sync 3, %0;" ::"n"(128 * MW) : "memory");
+      if (dq_issuer && !(dbg & 1)) {
+        asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                     ::"l"(&map_dq), "r"(sP), "r"(h * hd), "r"(tq * UB_BN), "r"(b) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    };
     for (int t = 0; t < T; ++t) {
       ua_mbar_wait(t_full + bo, t & 1);
       ua_fence_after();
@@ -343,6 +398,7 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
         if (row < 64 && t + 1 < T) my_stat = __ldg(pp_src + (t + 1) * UB_BN);
       } else if constexpr (KV) {
         float* sb = stat + (t % L::SB) * 128;
+        if (SP && dq_issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tile free again
         if (L::SB == 1) asm volatile("bar.sync 1, %0;" ::"n"(128 * MW) : "memory");   // previous tile's readers are done
         if (wg == 0) sb[row] = my_stat;
         asm volatile("bar.sync 1, %0;" ::"n"(128 * MW) : "memory");
@@ -373,7 +429,19 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
       }
       if (t > 0) ua_mbar_wait(o_done + bo, (t - 1) & 1);      // output MMAs of step t-1 done: P / dS smem is ours
       ua_fence_after();
-      if constexpr (TS) {
+      if constexpr (SP) { if (t > 0 && !(dbg & 2)) flush_dq(t - 1); }        // dQ tile of step t-1: TMEM -> staging -> TMA reduce-add
+      if constexpr (SP) {
+        // P^T -> tensor memory (A operand of dV), dS^T -> shared memory (A operand of dK, K-major, and of dQ, MN-major)
+        ua_st_regs<CW / 2>(t_1 + PT_COL + col0 / 2, pk_p);
+#pragma unroll
+        for (int c = 0; c < CW / 8; ++c) {
+          const uint32_t off = row * 128 + (((col0 / 8 + c) ^ (row & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + off), "r"(pk_d[4 * c]), "r"(pk_d[4 * c + 1]),
+                       "r"(pk_d[4 * c + 2]), "r"(pk_d[4 * c + 3]) : "memory");
+        }
+        ua_st_wait();
+        ua_fence_async_smem();
+      } else if constexpr (TS) {
         ua_st_regs<CW / 2>(t_1 + DST_COL + col0 / 2, pk_d);
         if constexpr (KV) ua_st_regs<CW / 2>(t_1 + PT_COL + col0 / 2, pk_p);
         ua_st_wait();
@@ -392,8 +460,16 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
       ua_fence_before();
       ua_mbar_arrive(p_full + bo);
     }
+    if constexpr (SP) {
+      if (dq_issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync 3, %0;" ::"n"(128 * MW) : "memory");
+    }
     ua_mbar_wait(all_done, 0);
     ua_fence_after();
+    if constexpr (SP) {
+      flush_dq(T - 1);
+      if (dq_issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
     // dqkv row layout [3][H][hd]: slot 0 = dQ, 1 = dK, 2 = dV
     bf16* drow = dqkv + ((int64_t)b * N + ri) * rs + (int64_t)h * hd;
 #pragma unroll
@@ -440,21 +516,27 @@ bool avj_attention_umma_bwd_supported(int dtype, int hd) {
   return dtype == AVJ_BF16 && hd % 8 == 0 && hd >= 8 && hd <= 64;
 }
 
-template <int HDP, bool TMA, bool KV, int MW, bool TS, bool PP>
-static int ub_launch(const CUtensorMap& m128, const CUtensorMap& m64, const CUtensorMap& mdo, const bf16* qkv, const bf16* dout,
+static int ub_dbg() {     // AVJ_ATTN_BWD_DBG (timing experiments only; results are WRONG when set): 1 = no TMA reduce, 2 = no dQ flush
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("AVJ_ATTN_BWD_DBG"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
+template <int HDP, bool TMA, bool KV, int MW, bool TS, bool PP, bool SP = false>
+static int ub_launch(const CUtensorMap& m128, const CUtensorMap& m64, const CUtensorMap& mdo, const CUtensorMap& mdq, const bf16* qkv, const bf16* dout,
                      const float* lse2, const float* delta, bf16* dqkv, int B, int N, int n_pad, int H, int hd, float scale,
                      cudaStream_t s) {
   static bool set = false;
   const int smem = (int)UbSmem<HDP, KV>::TOTAL;
   if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(fa_bwd_umma_kernel<HDP, TMA, KV, MW, TS, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(fa_bwd_umma_kernel<HDP, TMA, KV, MW, TS, PP, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     AVJ_CHECK(e == cudaSuccess, "cudaFuncSetAttribute(fa_bwd_umma_kernel) failed: %s", cudaGetErrorString(e));
-    cudaFuncSetAttribute(fa_bwd_umma_kernel<HDP, TMA, KV, MW, TS, PP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(fa_bwd_umma_kernel<HDP, TMA, KV, MW, TS, PP, SP>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     set = true;
   }
   dim3 grid((N + UB_BM - 1) / UB_BM, H, B);
-  avj_launch_pdl(fa_bwd_umma_kernel<HDP, TMA, KV, MW, TS, PP>, grid, dim3(128 + 128 * MW), (size_t)smem, s, m128, m64, mdo, qkv, dout, lse2, delta, dqkv, N, n_pad,
-                 H, hd, scale, scale * 1.4426950408889634f);
+  avj_launch_pdl(fa_bwd_umma_kernel<HDP, TMA, KV, MW, TS, PP, SP>, grid, dim3(128 + 128 * MW), (size_t)smem, s, m128, m64, mdo, mdq, qkv, dout, lse2, delta, dqkv, N, n_pad,
+                 H, hd, scale, scale * 1.4426950408889634f, ub_dbg());
   AVJ_LAUNCH_CHECK();
   return 0;
 }
@@ -471,9 +553,50 @@ static int ub_both(const bf16* qkv, const bf16* dout, const float* lse2, const f
     if ((rc = ua_make_map3d(dout, B, N, H * hd, 64, &mdo64, HDP))) return rc;
     if ((rc = ua_make_map3d(dout, B, N, H * hd, 128, &mdo128, HDP))) return rc;
   }
-  int rc = ub_launch<HDP, TMA, true, MW, TS, PP>(m128, m64, mdo64, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
+  int rc = ub_launch<HDP, TMA, true, MW, TS, PP>(m128, m64, mdo64, m128, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
   if (rc) return rc;
-  return ub_launch<HDP, TMA, false, MW, TS, PP>(m128, m64, mdo128, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
+  return ub_launch<HDP, TMA, false, MW, TS, PP>(m128, m64, mdo128, m128, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
+}
+
+// fp32 [B, N, cols] viewed as {cols, N, B}; box = {box_cols, box_rows, 1}, no swizzle (TMA reduce-add target of the dQ tiles)
+static int ub_make_map3d_f32(const void* ptr, int B, int N, int cols, int box_rows, int box_cols, CUtensorMap* out) {
+  typedef CUresult (*PFN)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                          const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static PFN enc = nullptr;
+  if (!enc) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      enc = reinterpret_cast<PFN>(p);
+  }
+  AVJ_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)N, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * 4, (cuuint64_t)cols * 4 * (cuuint64_t)N};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AVJ_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(dq accumulator) failed (%d)", (int)r);
+  return 0;
+}
+
+int avj_copy_rows(const void* in, int in_dtype, int ld_in, avj_rowmap imap, void* out, int out_dtype, int ld_out, avj_rowmap omap,
+                  int rows, int D, int accumulate, void* stream);
+
+// single pass (head_dim <= 32, TMA): zero the fp32 dQ accumulator, ONE kernel for dK / dV / dQ, then dQ -> bf16 into dqkv[..., 0, :, :]
+static int ub_single(const bf16* qkv, const bf16* dout, const float* lse2, const float* delta, bf16* dqkv, float* dq_acc,
+                     int B, int N, int n_pad, int H, int hd, float scale, cudaStream_t s) {
+  CUtensorMap m128, m64, mdo64, mdq;
+  memset(&m128, 0, sizeof(m128)); memset(&m64, 0, sizeof(m64)); memset(&mdo64, 0, sizeof(mdo64)); memset(&mdq, 0, sizeof(mdq));
+  int rc;
+  if ((rc = ua_make_map3d(qkv, B, N, 3 * H * hd, 128, &m128, 32))) return rc;
+  if ((rc = ua_make_map3d(qkv, B, N, 3 * H * hd, 64, &m64, 32))) return rc;
+  if ((rc = ua_make_map3d(dout, B, N, H * hd, 64, &mdo64, 32))) return rc;
+  if ((rc = ub_make_map3d_f32(dq_acc, B, N, H * hd, 64, hd, &mdq))) return rc;
+  rc = ub_launch<32, true, true, 2, true, false, true>(m128, m64, mdo64, mdq, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
+  if (rc) return rc;
+  const avj_rowmap ident = {0, 0, 0};
+  return avj_copy_rows(dq_acc, AVJ_F32, H * hd, ident, dqkv, AVJ_BF16, 3 * H * hd, ident, B * N, H * hd, 0, s);
 }
 
 int avj_attention_bwd_umma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* ws,
@@ -482,8 +605,15 @@ int avj_attention_bwd_umma(const void* qkv, const void* out, const void* dout, c
   const int n_pad = (N + 63) / 64 * 64;
   float* delta = ws;
   float* lse2 = ws + (int64_t)B * H * n_pad;
+  float* dq_acc = lse2 + (int64_t)B * H * n_pad;                 // [B, N, H, hd] fp32 (single-pass path)
+  static int sp = -1;          // AVJ_ATTN_BWD_SP=0: two passes (KV pass + Q pass) for head_dim <= 32 as well
+  if (sp < 0) { const char* e = getenv("AVJ_ATTN_BWD_SP"); sp = (e && e[0] == '0') ? 0 : 1; }
+  const bool al16 = ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(dout)) & 15) == 0;
+  const bool single = sp && hd <= 32 && al16 && (reinterpret_cast<uintptr_t>(dq_acc) & 15) == 0;
+  if (single) AVJ_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)B * N * H * hd * sizeof(float), s));
   int rc = avj_attention_delta(out, dout, delta, lse, lse2, scale, n_pad, B, N, H, hd, s);
   if (rc) return rc;
+  if (single) return ub_single((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, dq_acc, B, N, n_pad, H, hd, scale, s);
   static int use_tma = -1;
   if (use_tma < 0) { const char* e = getenv("AVJ_ATTN_TMA"); use_tma = (e && e[0] == '0') ? 0 : 1; }
   static int use_tma32 = -1;   // AVJ_ATTN_TMA32=0: head_dim <= 32 goes back to the cp.async gather loaders

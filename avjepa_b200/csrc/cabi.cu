@@ -162,8 +162,8 @@ extern "C" int avj_gemm(int dtype, int layout, const void* A, const void* B, voi
 }
 
 extern "C" int64_t avj_attention_bwd_ws_floats(int B, int N, int H, int hd) {
-  (void)hd;
-  return 2 * (int64_t)B * H * ((N + 63) / 64 * 64);   // delta and lse*log2(e), rows padded to 64
+  // delta and lse*log2(e) with rows padded to 64, plus the fp32 dQ accumulator [B, N, H, hd] of the single-pass kernel
+  return 2 * (int64_t)B * H * ((N + 63) / 64 * 64) + (int64_t)B * N * H * hd;
 }
 
 extern "C" int avj_attention_fwd(int dtype, const void* qkv, void* out, float* lse,

@@ -98,6 +98,8 @@ PROTOTYPES = {
     'avj_attention_fwd': (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     'avj_attention_bwd_ws_floats': (_i64, [_i, _i, _i, _i]),
     'avj_attention_bwd': (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    'avj_xattn_fwd': (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    'avj_xattn_bwd': (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     'avj_loss_ws_floats': (_i64, [_i64]),
     'avj_loss_fwd_bwd': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _f, _i, _f, _f, _vp, _vp]),
     'avj_reg_accumulate': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

@@ -1,7 +1,7 @@
 """Transformer building blocks: parameter containers with the reference's names and shapes.
 
 Mirror of ``src/models/utils/modules.py`` (``MLP :13-36``, ``Attention :39-78``,
-``Block :81-120``).  The sub-modules are ordinary ``nn.Linear`` / ``nn.LayerNorm`` holders so
+``Block :81-120``, ``CrossAttention :123-159``, ``CrossAttentionBlock :162-183``).  The sub-modules are ordinary ``nn.Linear`` / ``nn.LayerNorm`` holders so
 state-dict keys, parameter order (and therefore same-seed initialisation and the optimizer's
 name filters) are identical to the reference; the arithmetic does not go through their
 ``forward`` -- a backbone runs all of its blocks as one explicit kernel schedule
@@ -63,3 +63,38 @@ class Block(nn.Module):
             raise NotImplementedError('return_attention is not available from the fused attention kernel')
         from avjepa_b200 import backbone
         return backbone.run_blocks(self, [self], None, x)
+
+
+class CrossAttention(nn.Module):
+    """Parameter container of the reference's cross-attention (``q``, ``kv``, ``proj`` Linears); used on its own it is the
+    ``complete_block=False`` form of the attentive pooler."""
+
+    def __init__(self, dim, num_heads=12, qkv_bias=False, use_sdpa=True):
+        super().__init__()
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        self.scale = head_dim ** -0.5
+        self.q = nn.Linear(dim, dim, bias=qkv_bias)
+        self.kv = nn.Linear(dim, int(dim * 2), bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+        self.use_sdpa = use_sdpa
+
+    def forward(self, q, x):
+        from avjepa_b200 import pooler
+        return pooler.run_cross_attention(self, None, q, x)
+
+
+class CrossAttentionBlock(nn.Module):
+
+    def __init__(self, dim, num_heads, mlp_ratio=4., qkv_bias=False, act_layer=nn.GELU, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.norm1 = norm_layer(dim)
+        self.xattn = CrossAttention(dim, num_heads=num_heads, qkv_bias=qkv_bias)
+        self.norm2 = norm_layer(dim)
+        self.mlp = MLP(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer)
+
+    def forward(self, q, x):
+        """q: [B, n, D] queries, x: [B, N, D] encoder tokens -> [B, n, D]:
+        ``q + xattn(q, norm1(x))`` then ``+ mlp(norm2(.))`` (``modules.py:179-183``)."""
+        from avjepa_b200 import pooler
+        return pooler.run_cross_attention(self.xattn, self, q, x)

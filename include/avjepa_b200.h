@@ -141,11 +141,23 @@ int avj_layernorm_bwd(const void* dy, int dy_dtype, const float* x, const float*
  *      read in place (no permute copies); out is [B, N, H*hd]; lse fp32 [B, H, N]. */
 int avj_attention_fwd(int dtype, const void* qkv, void* out, float* lse,
                       int B, int N, int H, int hd, float scale, void* stream);
-/* dqkv [B, N, 3, H, hd];  ws: avj_attention_bwd_ws_floats(B,N,H,hd) floats. */
+/* dqkv [B, N, 3, H, hd];  ws: avj_attention_bwd_ws_floats(B,N,H,hd) floats (row statistics and, for head_dim <= 32,
+ * the fp32 dQ accumulator [B, N, H, hd] of the single-pass kernel: dK / dV / dQ from ONE evaluation of every exp2, the
+ * dQ tiles reduced across key blocks with TMA reduce-add). */
 int64_t avj_attention_bwd_ws_floats(int B, int N, int H, int hd);
 int avj_attention_bwd(int dtype, const void* qkv, const void* out, const void* dout,
                       const float* lse, void* dqkv, float* ws,
                       int B, int N, int H, int hd, float scale, void* stream);
+
+/* ---- few-query cross-attention of the attentive probes (src/models/attentive_pooler.py:21-102 ->
+ *      CrossAttention.forward, src/models/utils/modules.py:139-159): n learned queries over N encoder tokens, scale hd^-0.5.
+ *      q [B, n, H, hd] (q-Linear output), kv [B, N, 2, H, hd] (kv-Linear output, read in place), out [B, n, H*hd],
+ *      lse fp32 [B, H, n].  HBM-bound by construction (every K / V row is read once per (batch, head)).
+ *      bwd: dq [B, n, H, hd], dkv [B, N, 2, H, hd] (fully overwritten). */
+int avj_xattn_fwd(int dtype, const void* q, const void* kv, void* out, float* lse,
+                  int B, int N, int n, int H, int hd, float scale, void* stream);
+int avj_xattn_bwd(int dtype, const void* q, const void* kv, const void* out, const void* dout, const float* lse,
+                  void* dq, void* dkv, int B, int N, int n, int H, int hd, float scale, void* stream);
 
 /* ---- K10: latent loss sum_i mean(|z_i - h_i|^p)/p / n_masks (app/avjepa/train.py:490-495)
  *      for ONE mask, forward + backward in one pass.  z, h fp32 [n].

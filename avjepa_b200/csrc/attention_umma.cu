@@ -39,14 +39,19 @@
 // have 64-byte rows (UaTile) and afford 4 stages next to a second CTA; at hd = 64 there is room for 3 once P lives
 // in tensor memory (TS) and its 32 KB of shared memory are gone.
 template <int HDP, bool TS> struct UaSmem {
-  static constexpr int NST = HDP == 32 ? 4 : (TS ? 3 : 2);
-  static constexpr uint32_t TILE = 128 * UaTile<HDP>::PITCH;
+  static constexpr int NST = HDP == 32 ? 4 : (HDP == 128 ? 2 : (TS ? 3 : 2));
+  static constexpr uint32_t HALF = 128 * UaTile<HDP>::PITCH;            // one 64-column (or 32-column) sub-tile
+  static constexpr uint32_t TILE = HALF * UaTile<HDP>::NH;
   static constexpr uint32_t Q = 0, K = TILE, V = K + NST * TILE, P = V + NST * TILE, BARS = P + (TS ? 0 : 2 * UA_P_TILE),
                             TOTAL = BARS + 256;
 };
-#define UA_TMEM_COLS 256
 #define UA_O_COL 128
-#define UA_P_COL 192               // TS: 64 columns of packed bf16 P (128 keys)
+// TMEM: S 128 columns | O HDP columns | (TS) 64 columns of packed bf16 P.  256 columns (two CTAs per SM) up to HDP = 64;
+// HDP = 128 needs 320 -> a 512-column allocation, one CTA per SM (its 160 KB of shared memory allow no second one anyway).
+template <int HDP> struct UaTmem {
+  static constexpr uint32_t COLS = HDP == 128 ? 512 : 256;
+  static constexpr uint32_t P_COL = HDP == 128 ? 256 : 192;
+};
 
 // TMA = true (hd == 64): one elected thread issues 16 KB box loads (rows past N are zero-filled by
 // the hardware); TMA = false: the loader warp gathers 16-byte chunks with cp.async and pads in smem.
@@ -63,6 +68,9 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
   using TL = UaTile<HDP>;
   constexpr int NST = L::NST;
   constexpr uint32_t UA_TILE_BYTES = L::TILE;
+  constexpr int NH = TL::NH;
+  constexpr uint32_t UA_TMEM_COLS = UaTmem<HDP>::COLS, UA_P_COL = UaTmem<HDP>::P_COL;
+  static_assert(HDP != 128 || (TMA && TS), "head_dim > 64 runs the TMA loaders with P in tensor memory only");
   const uint32_t sQ = base + L::Q;
   const uint32_t sK = base + L::K;                   // [NST]
   const uint32_t sV = base + L::V;                   // [NST]
@@ -84,7 +92,8 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
   // A TMA box always spans HDP columns: for hd < HDP columns [hd, HDP) of every tile hold the NEXT head's
   // values.  They only matter in the contraction of S = Q K^T, so zeroing them in the Q tile is enough; the
   // matching columns of O = P V are computed from V's neighbour and never stored.
-  const bool zero_q_pad = TMA && hd < HDP;
+  // (HDP = 128: head_dim is a multiple of 16 and the score MMAs simply stop after hd / 16 K-steps.)
+  const bool zero_q_pad = TMA && hd < HDP && HDP != 128;
   const int64_t rs = 3 * (int64_t)H * hd;
   const bf16* qb = qkv + (int64_t)b * N * rs + (int64_t)h * hd;
   const bf16* kb = qb + (int64_t)H * hd;
@@ -122,9 +131,12 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
           if (t >= NST) ua_mbar_wait(kv_empty + 8 * st, ((t / NST) & 1) ^ 1);
           const uint32_t fb = kv_full + 8 * st;
           ua_expect_tx(fb, (t == 0 ? 3 : 2) * UA_TILE_BYTES);
-          if (t == 0) ua_tma3d(sQ, &tmap, fb, cq, q0, b);
-          ua_tma3d(sK + st * UA_TILE_BYTES, &tmap, fb, ck, t * UA_BN, b);
-          ua_tma3d(sV + st * UA_TILE_BYTES, &tmap, fb, cv, t * UA_BN, b);
+#pragma unroll
+          for (int hf = 0; hf < NH; ++hf) {                          // one box per 64-column half
+            if (t == 0) ua_tma3d(sQ + hf * L::HALF, &tmap, fb, cq + 64 * hf, q0, b);
+            ua_tma3d(sK + st * UA_TILE_BYTES + hf * L::HALF, &tmap, fb, ck + 64 * hf, t * UA_BN, b);
+            ua_tma3d(sV + st * UA_TILE_BYTES + hf * L::HALF, &tmap, fb, cv + 64 * hf, t * UA_BN, b);
+          }
         }
       }
     } else {
@@ -158,12 +170,18 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
     // ============================ MMA issuer ============================
     if (lane == 0) {
       const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UA_BN >> 3) << 17) | ((uint32_t)(UA_BM >> 4) << 24);
-      const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HDP >> 3) << 17) | ((uint32_t)(UA_BM >> 4) << 24);
+      const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)((HDP == 128 ? 64 : HDP) >> 3) << 17) |
+                               ((uint32_t)(UA_BM >> 4) << 24);
+      // HDP = 128: the second half of O has hd - 64 columns (16 .. 64)
+      const uint32_t idesc_o2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)((hd - 64) >> 3) << 17) | ((uint32_t)(UA_BM >> 4) << 24);
       const uint64_t qd = TL::kmajor(sQ);
+      const int ksteps = HDP == 128 ? hd / 16 : HDP / 16;
       auto issue_s = [&](int t) {
         const uint64_t kd = TL::kmajor(sK + (t % NST) * UA_TILE_BYTES);
-#pragma unroll
-        for (int k = 0; k < HDP / 16; ++k) ua_mma(tmem, qd + 2 * k, kd + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        for (int k = 0; k < ksteps; ++k) {
+          const uint32_t ho = (uint32_t)(k >> 2) * (L::HALF >> 4);     // descriptor offset of the half (16-byte units)
+          ua_mma(tmem, qd + ho + 2 * (k & 3), kd + ho + 2 * (k & 3), idesc_s, k > 0 ? 1u : 0u);
+        }
         ua_commit(s_full);
       };
       ua_mbar_wait(kv_full, 0);   // tile 0 (and Q)
@@ -186,6 +204,8 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
           const uint64_t vd = TL::mnmajor(vt) + TL::MN_KADV * k;     // MN-major: 16 keys per step
           if (TS) ua_mma_ts(tmem + UA_O_COL, tmem + UA_P_COL + 8 * k, vd, idesc_o, (t > 0 || k > 0) ? 1u : 0u);
           else    ua_mma(tmem + UA_O_COL, pd, vd, idesc_o, (t > 0 || k > 0) ? 1u : 0u);
+          if constexpr (HDP == 128)          // columns [64, hd) of O from the second V half
+            ua_mma_ts(tmem + UA_O_COL + 64, tmem + UA_P_COL + 8 * k, vd + (L::HALF >> 4), idesc_o2, (t > 0 || k > 0) ? 1u : 0u);
         }
         ua_commit(o_done);
         ua_commit(kv_empty + 8 * (t % NST));
@@ -297,6 +317,7 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
         float o[32];
 #pragma unroll
         for (int c = 0; c < HDP; c += 32) {
+          if (HDP == 128 && c >= hd) break;                          // columns past head_dim are never written
           ua_ld32(t_o + c, o);
           ua_ld_wait();
 #pragma unroll
@@ -318,6 +339,7 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
     bf16* orow = out + ((int64_t)b * N + qi) * (int64_t)H * hd + (int64_t)h * hd;
 #pragma unroll
     for (int c = 0; c < HDP; c += 32) {
+      if (HDP == 128 && c >= hd) break;
       float o[32];
       ua_ld32(t_o + c, o);
       ua_ld_wait();
@@ -348,7 +370,8 @@ fa_fwd_umma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restr
 // host
 // ------------------------------------------------------------------------------------------
 bool avj_attention_umma_fwd_supported(int dtype, int hd) {
-  return dtype == AVJ_BF16 && hd % 8 == 0 && hd >= 8 && hd <= 64;
+  // head_dim <= 64: multiples of 8 (padded to 32 / 64 in shared memory only); 80 .. 128: multiples of 16, two 64-column halves
+  return dtype == AVJ_BF16 && ((hd % 8 == 0 && hd >= 8 && hd <= 64) || (hd % 16 == 0 && hd > 64 && hd <= 128));
 }
 
 typedef CUresult (*PFN_ua_encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -405,7 +428,7 @@ static int ua_launch(const bf16* qkv, bf16* out, float* lse, int B, int N, int H
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
   if (TMA) {
-    int rc = ua_make_map3d(qkv, B, N, 3 * H * hd, 128, &map, HDP);
+    int rc = ua_make_map3d(qkv, B, N, 3 * H * hd, 128, &map, HDP == 128 ? 64 : HDP);
     if (rc) return rc;
   }
   dim3 grid((N + UA_BM - 1) / UA_BM, H, B);
@@ -436,6 +459,10 @@ int avj_attention_fwd_umma(const void* qkv, void* out, float* lse, int B, int N,
   if (hd <= 32) {
     if (use_tma32 && al) { UA_GO(32, true); }
     UA_GO(32, false);
+  }
+  if (hd > 64) {
+    AVJ_CHECK(al && use_tma, "attention forward: head_dim %d needs 16-byte aligned qkv (TMA loaders)", hd);
+    return ilv ? ua_launch<128, true, false, true, true>(UA_ARGS) : ua_launch<128, true, false, true, false>(UA_ARGS);
   }
   if (hd == 64 && use_tma && al) { UA_GO(64, true); }
   UA_GO(64, false);

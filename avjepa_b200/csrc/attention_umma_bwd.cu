@@ -42,7 +42,6 @@
 #define UB_BN 64
 #define UB_THREADS 256
 #define UB_LOADERS 96            // cp.async path: warps 0, 2, 3
-#define UB_TMEM_COLS 256
 #define UB_T2_COL 64
 #define UB_O1_COL 128
 #define UB_O2_COL 192
@@ -53,11 +52,13 @@
 // stages issue it one or two steps earlier.  hd <= 32 tiles are half the size (64-byte rows) so 4 stages
 // fit next to a second CTA; at hd = 64 there is room for 3 (112 KB per CTA in the dK/dV pass).
 template <int HDP, bool KV> struct UbSmem {
-  static constexpr int NST = HDP == 32 ? 4 : 3;
+  static constexpr int NST = HDP == 32 ? 4 : (HDP == 128 ? 2 : 3);
   // column-statistics buffers of the KV pass: two (one named barrier per step) where shared memory allows;
   // at hd = 64 two co-resident CTAs leave room for one (two barriers per step)
   static constexpr int SB = HDP == 32 ? 2 : 1;
-  static constexpr uint32_t ROW_TILE = 128 * UaTile<HDP>::PITCH, COL_TILE = 64 * UaTile<HDP>::PITCH;
+  // HDP = 128: every tile is two 64-column SWIZZLE_128B halves (RHALF / CHALF apart), 161 KB -> one CTA per SM
+  static constexpr uint32_t RHALF = 128 * UaTile<HDP>::PITCH, CHALF = 64 * UaTile<HDP>::PITCH;
+  static constexpr uint32_t ROW_TILE = RHALF * UaTile<HDP>::NH, COL_TILE = CHALF * UaTile<HDP>::NH;
   static constexpr uint32_t R1 = 0, R2 = ROW_TILE, C1 = 2 * ROW_TILE, C2 = C1 + NST * COL_TILE,
                             DS = C2 + NST * COL_TILE, P = DS + UB_PD_TILE,
                             STAT = KV ? P + UB_PD_TILE : P,            // KV pass: [SB][lse2 64 | delta 64] floats
@@ -91,10 +92,14 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
   using TL = UaTile<HDP>;
   constexpr int NST = L::NST;
   static_assert(!TS || HDP == 32, "operands in TMEM need the 256-column budget of HDP = 32");
+  static_assert(HDP != 128 || (TMA && !TS && !PP && !SP && MW == 2), "head_dim > 64: TMA loaders, operands through shared memory, two lockstep warpgroups");
+  constexpr int NH = TL::NH;
+  // TMEM: scores 2 x 64 | outputs 2 x HDP.  HDP = 128 needs 384 columns -> a 512-column allocation (one CTA per SM)
+  constexpr uint32_t UB_TMEM_COLS = HDP == 128 ? 512 : 256;
   static_assert(!PP || MW == 2, "the decoupled schedule needs two math warpgroups");
   static_assert(!SP || (KV && HDP == 32 && TMA && TS && MW == 2 && !PP), "single pass: KV pass, HDP 32, TMA, P^T in TMEM, two lockstep warpgroups");
   constexpr uint32_t DQ_COL = 224;                            // SP: dQ tile (M = 64: rows 16j + i sit in lane 32j + i)
-  constexpr uint32_t O1_COL = UB_O1_COL, O2_COL = TS ? UB_O1_COL + 32 : UB_O2_COL;
+  constexpr uint32_t O1_COL = UB_O1_COL, O2_COL = TS ? UB_O1_COL + 32 : (HDP == 128 ? UB_O1_COL + 128 : UB_O2_COL);
   constexpr uint32_t PT_COL = 192, DST_COL = 224;             // TS: packed bf16 P^T / dS^T, 32 columns each
   extern __shared__ __align__(1024) uint8_t ub_raw[];
   const uint32_t base = ua_smem(ub_raw);
@@ -128,7 +133,8 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
   // A TMA box always spans HDP columns: for hd < HDP columns [hd, HDP) hold the neighbouring head.  Both score
   // products contract over those columns with one STATIONARY operand (S: R1, dP: R2), so zeroing the pads of
   // R1 / R2 once per CTA is enough; the pad columns of dQ / dK / dV are never stored.
-  const bool zero_pad = TMA && hd < HDP;
+  // (HDP = 128: head_dim is a multiple of 16 and the score MMAs stop after hd / 16 K-steps instead.)
+  const bool zero_pad = TMA && hd < HDP && HDP != 128;
 
   if (threadIdx.x == 0) {
     if (base & 1023u) __trap();
@@ -182,14 +188,19 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
         if (lane == 0) {
           const uint32_t fb = c_full + 8 * st;
           ua_expect_tx(fb, 2 * L::COL_TILE + (t == 0 ? 2 * L::ROW_TILE : 0));
-          if (t == 0) {
-            ua_tma3d(sR1, &map_qkv128, fb, c_r1, r0, b);
-            if (KV) ua_tma3d(sR2, &map_qkv128, fb, (2 * H + h) * hd, r0, b);
-            else    ua_tma3d(sR2, &map_do, fb, h * hd, r0, b);
+#pragma unroll
+          for (int hf = 0; hf < NH; ++hf) {                       // one box per 64-column half
+            const int dc = 64 * hf;
+            const uint32_t ro = hf * L::RHALF, co = hf * L::CHALF;
+            if (t == 0) {
+              ua_tma3d(sR1 + ro, &map_qkv128, fb, c_r1 + dc, r0, b);
+              if (KV) ua_tma3d(sR2 + ro, &map_qkv128, fb, (2 * H + h) * hd + dc, r0, b);
+              else    ua_tma3d(sR2 + ro, &map_do, fb, h * hd + dc, r0, b);
+            }
+            ua_tma3d(c1 + co, &map_qkv64, fb, c_c1 + dc, t * UB_BN, b);
+            if (KV) ua_tma3d(c2 + co, &map_do, fb, h * hd + dc, t * UB_BN, b);
+            else    ua_tma3d(c2 + co, &map_qkv64, fb, (2 * H + h) * hd + dc, t * UB_BN, b);
           }
-          ua_tma3d(c1, &map_qkv64, fb, c_c1, t * UB_BN, b);
-          if (KV) ua_tma3d(c2, &map_do, fb, h * hd, t * UB_BN, b);
-          else    ua_tma3d(c2, &map_qkv64, fb, (2 * H + h) * hd, t * UB_BN, b);
         }
       } else {
         ua_stage<HDP, 64>(c1, KV ? qb : kb, rs, t * UB_BN, N, hd, ld_tid, ld_n);
@@ -215,15 +226,30 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
     // ============================ MMA issuer ============================
     if (lane == 0) {
       const uint32_t idesc_t = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UB_BN >> 3) << 17) | ((uint32_t)(UB_BM >> 4) << 24);
-      const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(HDP >> 3) << 17) | ((uint32_t)(UB_BM >> 4) << 24);
+      const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)((HDP == 128 ? 64 : HDP) >> 3) << 17) |
+                               ((uint32_t)(UB_BM >> 4) << 24);
+      // HDP = 128: columns [64, hd) of every output come from the second half of the streamed tile
+      const uint32_t idesc_o2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)((hd - 64) >> 3) << 17) | ((uint32_t)(UB_BM >> 4) << 24);
+      const int ksteps = HDP == 128 ? hd / 16 : HDP / 16;
       const uint64_t r1d = TL::kmajor(sR1), r2d = TL::kmajor(sR2);
       auto issue_scores = [&](int t) {
         const uint64_t c1d = TL::kmajor(sC1 + (t % NST) * L::COL_TILE);
         const uint64_t c2d = TL::kmajor(sC2 + (t % NST) * L::COL_TILE);
+        if constexpr (HDP == 128) {
+          for (int k = 0; k < ksteps; ++k) {
+            const uint32_t kr = (uint32_t)(k >> 2) * (L::RHALF >> 4) + 2 * (k & 3), kc = (uint32_t)(k >> 2) * (L::CHALF >> 4) + 2 * (k & 3);
+            ua_mma(tmem, r1d + kr, c1d + kc, idesc_t, k > 0 ? 1u : 0u);
+          }
+          for (int k = 0; k < ksteps; ++k) {
+            const uint32_t kr = (uint32_t)(k >> 2) * (L::RHALF >> 4) + 2 * (k & 3), kc = (uint32_t)(k >> 2) * (L::CHALF >> 4) + 2 * (k & 3);
+            ua_mma(tmem + UB_T2_COL, r2d + kr, c2d + kc, idesc_t, k > 0 ? 1u : 0u);
+          }
+        } else {
 #pragma unroll
-        for (int k = 0; k < HDP / 16; ++k) ua_mma(tmem, r1d + 2 * k, c1d + 2 * k, idesc_t, k > 0 ? 1u : 0u);
+          for (int k = 0; k < HDP / 16; ++k) ua_mma(tmem, r1d + 2 * k, c1d + 2 * k, idesc_t, k > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < HDP / 16; ++k) ua_mma(tmem + UB_T2_COL, r2d + 2 * k, c2d + 2 * k, idesc_t, k > 0 ? 1u : 0u);
+          for (int k = 0; k < HDP / 16; ++k) ua_mma(tmem + UB_T2_COL, r2d + 2 * k, c2d + 2 * k, idesc_t, k > 0 ? 1u : 0u);
+        }
         ua_commit(t_full);
       };
       // one column half (32 streamed rows) of both score products; PP only
@@ -268,12 +294,14 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
             const uint32_t acc = (t > 0 || k > 0) ? 1u : 0u;
             if (TS) ua_mma_ts(tmem + O1_COL, tmem + PT_COL + 8 * k, c2m + TL::MN_KADV * k, idesc_o, acc);
             else    ua_mma(tmem + O1_COL, pd + 2 * k, c2m + TL::MN_KADV * k, idesc_o, acc);
+            if constexpr (HDP == 128) ua_mma(tmem + O1_COL + 64, pd + 2 * k, c2m + (L::CHALF >> 4) + TL::MN_KADV * k, idesc_o2, acc);
           }
 #pragma unroll
           for (int k = k0; k < k1; ++k) {                                                      // dK += dS^T Q
             const uint32_t acc = (t > 0 || k > 0) ? 1u : 0u;
             if (TS) ua_mma_ts(tmem + O2_COL, tmem + DST_COL + 8 * k, c1m + TL::MN_KADV * k, idesc_o, acc);
             else    ua_mma(tmem + O2_COL, dsd + 2 * k, c1m + TL::MN_KADV * k, idesc_o, acc);
+            if constexpr (HDP == 128) ua_mma(tmem + O2_COL + 64, dsd + 2 * k, c1m + (L::CHALF >> 4) + TL::MN_KADV * k, idesc_o2, acc);
           }
           }
         } else {
@@ -282,6 +310,7 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
             const uint32_t acc = (t > 0 || k > 0) ? 1u : 0u;
             if (TS) ua_mma_ts(tmem + O1_COL, tmem + DST_COL + 8 * k, c1m + TL::MN_KADV * k, idesc_o, acc);
             else    ua_mma(tmem + O1_COL, dsd + 2 * k, c1m + TL::MN_KADV * k, idesc_o, acc);
+            if constexpr (HDP == 128) ua_mma(tmem + O1_COL + 64, dsd + 2 * k, c1m + (L::CHALF >> 4) + TL::MN_KADV * k, idesc_o2, acc);
           }
         }
       };
@@ -479,6 +508,7 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
 #pragma unroll
       for (int c = 0; c < HDP; c += 32) {
         if ((o * (HDP / 32) + c / 32) % MW != wg) continue;   // 32-column output blocks round-robin over the warpgroups
+        if (HDP == 128 && c >= hd) continue;                  // never written
         float v[32];
         ua_ld32(t_o + c, v);
         ua_ld_wait();
@@ -513,7 +543,8 @@ int avj_attention_delta(const void* out, const void* dout, float* delta, const f
 int ua_make_map3d(const void* ptr, int B, int N, int cols, int box_rows, CUtensorMap* out, int box_cols);
 
 bool avj_attention_umma_bwd_supported(int dtype, int hd) {
-  return dtype == AVJ_BF16 && hd % 8 == 0 && hd >= 8 && hd <= 64;
+  // head_dim <= 64: multiples of 8; 80 .. 128: multiples of 16 (two 64-column halves per tile)
+  return dtype == AVJ_BF16 && ((hd % 8 == 0 && hd >= 8 && hd <= 64) || (hd % 16 == 0 && hd > 64 && hd <= 128));
 }
 
 static int ub_dbg() {     // AVJ_ATTN_BWD_DBG (timing experiments only; results are WRONG when set): 1 = no TMA reduce, 2 = no dQ flush
@@ -548,10 +579,11 @@ static int ub_both(const bf16* qkv, const bf16* dout, const float* lse2, const f
   memset(&m128, 0, sizeof(m128)); memset(&m64, 0, sizeof(m64)); memset(&mdo64, 0, sizeof(mdo64)); memset(&mdo128, 0, sizeof(mdo128));
   if (TMA) {
     int rc;
-    if ((rc = ua_make_map3d(qkv, B, N, 3 * H * hd, 128, &m128, HDP))) return rc;
-    if ((rc = ua_make_map3d(qkv, B, N, 3 * H * hd, 64, &m64, HDP))) return rc;
-    if ((rc = ua_make_map3d(dout, B, N, H * hd, 64, &mdo64, HDP))) return rc;
-    if ((rc = ua_make_map3d(dout, B, N, H * hd, 128, &mdo128, HDP))) return rc;
+    constexpr int BC = HDP == 128 ? 64 : HDP;                   // box columns
+    if ((rc = ua_make_map3d(qkv, B, N, 3 * H * hd, 128, &m128, BC))) return rc;
+    if ((rc = ua_make_map3d(qkv, B, N, 3 * H * hd, 64, &m64, BC))) return rc;
+    if ((rc = ua_make_map3d(dout, B, N, H * hd, 64, &mdo64, BC))) return rc;
+    if ((rc = ua_make_map3d(dout, B, N, H * hd, 128, &mdo128, BC))) return rc;
   }
   int rc = ub_launch<HDP, TMA, true, MW, TS, PP>(m128, m64, mdo64, m128, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
   if (rc) return rc;
@@ -635,6 +667,10 @@ int avj_attention_bwd_umma(const void* qkv, const void* out, const void* dout, c
     if (use_tma32 && aligned) { if (ts) { UB_GO(32, true, true); } UB_GO(32, true, false); }
     if (ts) { UB_GO(32, false, true); }
     UB_GO(32, false, false);
+  }
+  if (hd > 64) {
+    AVJ_CHECK(aligned && use_tma, "attention backward: head_dim %d needs 16-byte aligned qkv / dout (TMA loaders)", hd);
+    return ub_both<128, true, 2, false, false>(UB_ARGS);
   }
   if (hd == 64 && use_tma && aligned) { UB_GO(64, true, false); }
   UB_GO(64, false, false);

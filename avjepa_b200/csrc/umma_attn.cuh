@@ -39,7 +39,10 @@ __device__ __forceinline__ uint64_t ua_desc(uint32_t saddr, uint32_t lbo16, uint
 
 // Geometry of an operand tile whose rows hold HDP bf16 of one head: HDP = 64 -> 128-byte rows, SWIZZLE_128B;
 // HDP = 32 -> 64-byte rows, SWIZZLE_64B (half the shared memory and L2 traffic of padding to 128 bytes).
+// HDP = 128 (head_dim 80 .. 128): TWO 64-column SWIZZLE_128B sub-tiles ("halves") of 128 rows each, HALF bytes apart; the
+// geometry constants below describe one half.
 template <int HDP> struct UaTile {
+  static constexpr int NH = HDP == 128 ? 2 : 1;                      // 64-column halves per tile
   static constexpr int PITCH = HDP == 32 ? 64 : 128;                 // bytes per row
   static constexpr uint32_t LAYOUT = HDP == 32 ? 4u : 2u;            // descriptor layout type
   static constexpr uint32_t SBO = 8 * PITCH / 16;                    // 8-row group stride, 16-byte units

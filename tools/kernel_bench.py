@@ -204,6 +204,10 @@ if __name__ == '__main__':
         bench_attn(24, 1664, 16, 64, 'target enc')
         bench_attn(24, 384, 16, 64, 'ctx enc')
         bench_attn(24, 1216, 16, 24, 'predictor')
+    if which == 'attn_h':                               # ViT-H (config 4): 16 heads of 80
+        bench_attn(24, 1664, 16, 80, 'vit_huge target enc')
+        bench_attn(24, 384, 16, 80, 'vit_huge ctx enc')
+        bench_attn(8, 1664, 16, 128, 'hd128')
     if which in ('all', 'misc'):
         bench_ln(R_T, 1024)
         bench_ln(24 * 537, 1024)

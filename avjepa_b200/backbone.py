@@ -76,6 +76,14 @@ def _pos_table(mod, x, name):
     return _f32c(pos)
 
 
+def _patchify(x5, idx, B, K, tub, p, mode):
+    """[B*K, C*tub*p*p] patch matrix of the kept tokens in the compute dtype (avj_patchify)."""
+    _, Cin, T, H, W = x5.shape
+    out = torch.empty((B * K, Cin * tub * p * p), dtype=mode.torch_dtype, device=x5.device)
+    _cabi.call('avj_patchify', x5.data_ptr(), _ptr(idx), out.data_ptr(), mode.code, B, Cin, T, H, W, tub, p, K, stream())
+    return out
+
+
 def encoder_forward(mod, x, y, masks, save, mode):
     """`masks`: list of (video_idx, audio_idx) pairs, one per mask (entries None = keep every token); `y` and the
     audio indices are None for the video-only encoder.  ALL masks run through one variable-length stack
@@ -115,25 +123,38 @@ def encoder_forward(mod, x, y, masks, save, mode):
     pos_a = _f32c(mod.audio_pos_embed) if y is not None else None
     kd_v = Cin * tub * p * p
     pe = mod.patch_embed
+    lib = _cabi.load()
+    # bf16 mode: im2col-free tf32 kernel (the patch rows go from the clip to the tensor cores by TMA); fp32 check mode
+    # and odd geometries: patch matrix + GEMM
+    tma_ok = mode.code == _cabi.BF16 and engine.patch_embed_tma_enabled()
     st.patches = []
     for g, (mv, ma, Kv, Ka) in enumerate(groups):
         N = Kv + Ka
         x0 = run.x0_rows(g)
-        pv = torch.empty((B * Kv, kd_v), dtype=mode.torch_dtype, device=dev)
-        _cabi.call('avj_patchify', x5.data_ptr(), _ptr(mv), pv.data_ptr(), cd, B, Cin, T, H, W, tub, p, Kv, stream())
-        engine.gemm(mode, GEMM_NT, pv.data_ptr(), _wptr(pe.proj.weight, mod, mode), x0,
-                    B * Kv, D, kd_v, kd_v, kd_v, D, F32, bias=_ptr(pe.proj.bias), pos=pos_v.data_ptr(),
-                    pos_idx=_ptr(mv), pos_rows=pos_v.shape[1], out_map=rowmap(Kv, N, 0))
+        pv = None
+        if tma_ok and lib.avj_patch_embed_supported(p, H, W, T, tub, D):
+            engine.patch_embed(x5.data_ptr(), _ptr(mv), _f32c(pe.proj.weight).data_ptr(), x0, B, Cin, T, H, W, tub, p, Kv, D, D,
+                               bias=_ptr(pe.proj.bias), pos=pos_v.data_ptr(), pos_idx=_ptr(mv), pos_rows=pos_v.shape[1],
+                               out_map=rowmap(Kv, N, 0))
+        else:
+            pv = _patchify(x5, mv, B, Kv, tub, p, mode)
+            engine.gemm(mode, GEMM_NT, pv.data_ptr(), _wptr(pe.proj.weight, mod, mode), x0,
+                        B * Kv, D, kd_v, kd_v, kd_v, D, F32, bias=_ptr(pe.proj.bias), pos=pos_v.data_ptr(),
+                        pos_idx=_ptr(mv), pos_rows=pos_v.shape[1], out_map=rowmap(Kv, N, 0))
         pa = None
         if y is not None and Ka > 0:
             kd_a = y.shape[1] * p * p
-            pa = torch.empty((B * Ka, kd_a), dtype=mode.torch_dtype, device=dev)
-            _cabi.call('avj_patchify', y.data_ptr(), _ptr(ma), pa.data_ptr(), cd, B, y.shape[1], 1, y.shape[2],
-                       y.shape[3], 1, p, Ka, stream())
-            engine.gemm(mode, GEMM_NT, pa.data_ptr(), _wptr(pe.audio_proj.weight, mod, mode), x0,
-                        B * Ka, D, kd_a, kd_a, kd_a, D, F32, bias=_ptr(pe.audio_proj.bias), pos=pos_a.data_ptr(),
-                        pos_idx=_ptr(ma), pos_rows=pos_a.shape[1], out_map=rowmap(Ka, N, Kv))
-        st.patches.append((pv, pa) if save else (None, None))
+            if tma_ok and lib.avj_patch_embed_supported(p, y.shape[2], y.shape[3], 1, 1, D):
+                engine.patch_embed(y.data_ptr(), _ptr(ma), _f32c(pe.audio_proj.weight).data_ptr(), x0, B, y.shape[1], 1, y.shape[2],
+                                   y.shape[3], 1, p, Ka, D, D, bias=_ptr(pe.audio_proj.bias), pos=pos_a.data_ptr(),
+                                   pos_idx=_ptr(ma), pos_rows=pos_a.shape[1], out_map=rowmap(Ka, N, Kv))
+            else:
+                pa = _patchify(y.unsqueeze(2), ma, B, Ka, 1, p, mode)
+                engine.gemm(mode, GEMM_NT, pa.data_ptr(), _wptr(pe.audio_proj.weight, mod, mode), x0,
+                            B * Ka, D, kd_a, kd_a, kd_a, D, F32, bias=_ptr(pe.audio_proj.bias), pos=pos_a.data_ptr(),
+                            pos_idx=_ptr(ma), pos_rows=pos_a.shape[1], out_map=rowmap(Ka, N, Kv))
+        st.patches.append((pv, pa))
+    st.geom = (tub, p)
     st.keep = (x5, y, [g_[:2] for g_ in groups], pos_v, pos_a)       # keep inputs alive until the kernels reading them retire
     sh = _shadows(mod)
     blocks = [BlockW(b, sh, mode, False) for b in mod.blocks]
@@ -188,11 +209,19 @@ def encoder_backward(mod, st, douts):
     for g, (mv, ma, Kv, Ka) in enumerate(st.groups):
         N = Kv + Ka
         dx0_g = dx0 + run.row0[g] * D * 4
-        for (K, off, patches, conv) in ((Kv, 0, st.patches[g][0], pe.proj), (Ka, Kv, st.patches[g][1], getattr(pe, 'audio_proj', None))):
-            if K == 0 or patches is None or conv is None:
+        x5, y = st.keep[0], st.keep[1]
+        tub, p = st.geom
+        for (K, off, patches, conv, src, idx, tb) in ((Kv, 0, st.patches[g][0], pe.proj, x5, mv, tub),
+                                                      (Ka, Kv, st.patches[g][1], getattr(pe, 'audio_proj', None),
+                                                       y.unsqueeze(2) if y is not None else None, ma, 1)):
+            if K == 0 or conv is None or src is None:
                 continue
             gw, gb = engine.grad_ptr(conv.weight), engine.grad_ptr(conv.bias) if conv.bias is not None else None
-            kd = patches.shape[1]
+            if patches is None and gw is not None:
+                # the forward embedded the tokens straight out of the clip; the weight gradient's second operand (kept tokens
+                # only, 2 % of the clip at 90 % masking) is gathered here, where it is consumed
+                patches = _patchify(src, idx, B, K, tb, p, mode)
+            kd = conv.weight[0].numel()
             rm = rowmap(K, N, off)
             if gb is not None:
                 engine.colsum(dx0_g, F32, D, rm, gb, B * K, D, ws)

@@ -161,6 +161,25 @@ extern "C" int avj_gemm(int dtype, int layout, const void* A, const void* B, voi
   return avj_gemm_simt(dtype, layout, A, B, C, M, N, K, lda, ldb, ldc, ep, as_stream(stream));
 }
 
+bool avj_patch_embed_umma_supported(int patch, int H, int W, int T, int tub, int D);
+int avj_patch_embed_umma(const float* x, const int64_t* idx, const float* w, float* out, int B, int C, int T, int H, int W, int tub,
+                         int patch, int Kt, int D, int ldc, const avj_epilogue& ep, cudaStream_t s);
+
+extern "C" int avj_patch_embed_supported(int patch, int H, int W, int T, int tub, int D) {
+  return avj_patch_embed_umma_supported(patch, H, W, T, tub, D) ? 1 : 0;
+}
+
+extern "C" int avj_patch_embed(const float* x, const int64_t* idx, const float* w, float* out,
+                               int B, int C, int T, int H, int W, int tub, int patch, int K, int D, int ldc,
+                               const avj_epilogue* ep, void* stream) {
+  AVJ_CHECK(ep != nullptr, "avj_patch_embed: epilogue must not be NULL");
+  if (B == 0 || K == 0) return 0;
+  const int kd = C * tub * patch * patch;
+  // profiled as a GEMM (NT, bias, fp32 out) of M = B*K, N = D, K = kd
+  AvjProfScope prof(AVJ_FAM_GEMM, 2.0 * B * K * (double)D * kd, stream, 0 | 4 | 128 | 256, B * K, D, kd);
+  return avj_patch_embed_umma(x, idx, w, out, B, C, T, H, W, tub, patch, K, D, ldc, *ep, as_stream(stream));
+}
+
 extern "C" int64_t avj_attention_bwd_ws_floats(int B, int N, int H, int hd) {
   // delta and lse*log2(e) with rows padded to 64, plus the fp32 dQ accumulator [B, N, H, hd] of the single-pass kernel
   return 2 * (int64_t)B * H * ((N + 63) / 64 * 64) + (int64_t)B * N * H * hd;

@@ -43,6 +43,14 @@ struct UmmaParams {
   uint32_t mn_lbo, mn_sbo, mn_kadv;   // MN-major descriptor fields / k-advance (16 B units)
   void* C;
   int tma_store;         // thread==row epilogues: bf16 C (and pre_out) leave through smem + TMA bulk stores
+  // ---- im2col-free patch embedding (gemm_umma_kernel<..., IM2COL = true> only): A rows are tokens whose 16 x 16 patch
+  //      rows are gathered straight out of the clip / spectrogram into the operand tile; both operands are fp32 in
+  //      shared memory and the MMA is kind::tf32 (k-block = 32 elements = two patch rows of one (channel, frame))
+  const float* ic_x;     // [B, C, T, H, W]
+  const int64_t* ic_idx; // [B, ic_kt] kept-token ids (sorted), or nullptr: every token, ic_kt == tokens per sample
+  int ic_kt;             // GEMM rows per sample
+  int ic_nw, ic_nh;      // tokens per frame row / frame column
+  int ic_tub, ic_c, ic_t;// tubelet depth, channels, frames
   avj_epilogue ep;
 };
 
@@ -103,6 +111,16 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
       "}\n"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
@@ -390,7 +408,7 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, const CUtenso
 // EW = number of epilogue warps: 8 (two per TMEM lane quarter, half of the columns each) or 16 (four per
 // quarter, a quarter of the columns each) for the thread==row epilogues, which are latency- rather than
 // issue-bound and double their throughput with twice the warps in flight.
-template <int EPI, int EW, bool TS>
+template <int EPI, int EW, bool TS, bool IM2COL = false>
 __global__ void __launch_bounds__(128 + 32 * EW, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_p, const UmmaParams p) {
@@ -414,7 +432,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
-    for (int i = 0; i < UG_STAGES; ++i) { mbar_init(full_bar + 8 * i, 1); mbar_init(empty_bar + 8 * i, 1); }
+    for (int i = 0; i < UG_STAGES; ++i) { mbar_init(full_bar + 8 * i, IM2COL ? 97 : 1); mbar_init(empty_bar + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + 8 * i, 1); mbar_init(tempty_bar + 8 * i, 32 * EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -431,9 +449,74 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const int n_units = p.tiles_m * p.tiles_n * p.split_k;
 
   if (warp < 4) {
-    // warpgroup 0 hands its registers to the epilogue warpgroups (the kernel is compiled for 168)
-    reg_dec<40>();
-    if (warp == 0) {
+    // warpgroup 0 hands its registers to the epilogue warpgroups (the kernel is compiled for 168); the gather loop of
+    // the im2col producer needs more than 40, so that instantiation keeps the launch allocation everywhere
+    if constexpr (!IM2COL) reg_dec<40>();
+    if (IM2COL && warp != 1) {
+      // ================= producer, im2col-free patch rows (warps 0, 2, 3: 96 threads) =================
+      // Row r of the A tile is one token; its k-block kb is 128 bytes: rows dh0, dh0 + 1 (16 floats each) of the token's
+      // 16 x 16 patch in (channel c, frame dt of the tubelet), kb = ((c * tub + dt) * 16 + dh0) / 2 -- exactly the
+      // (c, dt, dh, dw) order of the Conv3d / Conv2d weight.  Those are 64-byte runs 4*W bytes apart: as TMA boxes they
+      // are far too small (measured: ~65 clk per box, 6 x slower than the tensor pipe needs), so the gather is 16-byte
+      // cp.async copies straight into the SWIZZLE_128B K-major tile (thread = one 16-byte chunk column of 11 rows); the
+      // weight tile comes by TMA as usual.  A stage is published two commits later: cp.async.wait_group, proxy fence,
+      // arrive -- full barrier = 96 thread arrivals + the expect_tx arrival of the weight box.
+      const int pt = warp == 0 ? lane : (warp - 1) * 32 + lane;      // 0 .. 95
+      const int ch = pt & 7, rg = pt >> 3;                             // chunk of the 128-byte row; rows rg, rg + 12, ...
+      const int in_row = (ch >> 2), dw0 = (ch & 3) * 4;                // which of the two patch rows, first float
+      const uint32_t b_box_bytes = (uint32_t)p.block_n * 128u;
+      const int HW = p.ic_nh * 16 * p.ic_nw * 16, Wd = p.ic_nw * 16;
+      constexpr int LAG = 2;
+      uint32_t stage = 0, phase = 0;
+      int issued = 0;
+      auto publish = [&](int which) { mbar_arrive(full_bar + 8 * (which % UG_STAGES)); };
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int tile = u / p.split_k, ks = u % p.split_k;
+        const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+        int base[11];                                                  // element offset of (token, plane 0, patch row 0, dw0)
+#pragma unroll
+        for (int i = 0; i < 11; ++i) {
+          const int r = rg + 12 * i;
+          int row = m_blk * UG_BM + r;
+          row = min(row, p.M - 1);                                     // rows past M re-load the last token (never stored)
+          const int b = row / p.ic_kt, jj = row % p.ic_kt;
+          const int tok = p.ic_idx ? (int)__ldg(p.ic_idx + (int64_t)b * p.ic_kt + jj) : jj;
+          const int wt = tok % p.ic_nw, hrow = tok / p.ic_nw;
+          base[i] = ((b * p.ic_c) * p.ic_t + (hrow / p.ic_nh) * p.ic_tub) * HW + (hrow % p.ic_nh) * 16 * Wd + wt * 16 + dw0;
+        }
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int plane = kb >> 3;                                   // (c, dt): 8 k-blocks of two patch rows each
+          const int off = ((plane / p.ic_tub) * p.ic_t + plane % p.ic_tub) * HW + ((kb & 7) * 2 + in_row) * Wd;
+          const uint32_t fb = full_bar + 8 * stage;
+          const uint32_t sa = smem_a + stage * UG_A_STAGE_BYTES;
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          if (pt == 0) {
+            mbar_expect_tx(fb, b_box_bytes);
+            tma_load_2d(smem_b + stage * UG_B_STAGE_BYTES, &tma_b, fb, kb * 32, n_blk * p.block_n);
+          }
+#pragma unroll
+          for (int i = 0; i < 11; ++i) {
+            const int r = rg + 12 * i;
+            if (r < UG_BM) {
+              const uint32_t dst = sa + (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4);
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(p.ic_x + base[i] + off) : "memory");
+            }
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          if (++issued > LAG) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(LAG) : "memory");
+            fence_proxy_async_smem();
+            publish(issued - 1 - LAG);
+          }
+          if (++stage == UG_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      fence_proxy_async_smem();
+      for (int j = max(0, issued - LAG); j < issued; ++j) publish(j);
+    } else if (warp == 0) {
       // ================= TMA producer =================
       if (lane == 0) {
         const uint32_t b_box_bytes = (uint32_t)p.block_n * UG_BK * 2;
@@ -468,7 +551,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     } else if (warp == 1) {
       // ================= MMA issuer =================
       if (lane == 0) {
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn_major << 15) |
+        // operand format field: 1 = bf16 (kind::f16), 2 = tf32 (kind::tf32); fp32 accumulator
+        const uint32_t fmt = IM2COL ? 2u : 1u;
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)p.a_mn_major << 15) |
                                ((uint32_t)p.b_mn_major << 16) | ((uint32_t)(p.block_n >> 3) << 17) |
                                ((uint32_t)(UG_BM >> 4) << 24);
         uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
@@ -489,9 +574,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const uint32_t a_adv = p.a_mn_major ? p.mn_kadv : 2u;   // 16-byte units per UMMA_K=16
             const uint32_t b_adv = p.b_mn_major ? p.mn_kadv : 2u;
 #pragma unroll
-            for (int k = 0; k < UG_BK / 16; ++k) {
-              tc_mma_bf16(tmem_d, adesc0 + (uint64_t)(k * a_adv), bdesc0 + (uint64_t)(k * b_adv), idesc,
-                          (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < UG_BK / 16; ++k) {             // tf32: 4 steps of K = 8 elements, also 32 bytes each
+              if (IM2COL) tc_mma_tf32(tmem_d, adesc0 + (uint64_t)(k * a_adv), bdesc0 + (uint64_t)(k * b_adv), idesc,
+                                      (kb > kb0 || k > 0) ? 1u : 0u);
+              else tc_mma_bf16(tmem_d, adesc0 + (uint64_t)(k * a_adv), bdesc0 + (uint64_t)(k * b_adv), idesc,
+                               (kb > kb0 || k > 0) ? 1u : 0u);
             }
             tc_commit(empty_bar + 8 * stage);          // frees the smem stage when these MMAs retire
             if (++stage == UG_STAGES) { stage = 0; phase ^= 1; }
@@ -504,7 +591,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   } else {
     // ================= epilogue warpgroups (EW warps) =================
     // EW/4 warps per TMEM lane quarter, each taking BN/(EW/4) of the tile's columns, 32 columns at a time.
-    reg_inc<EW == 8 ? 232 : 104>();   // pool: 640 x 96 at launch; 128 x (96 - 40) freed >= 512 x (104 - 96) claimed (112 would deadlock)
+    if constexpr (!IM2COL) reg_inc<EW == 8 ? 232 : 104>();   // pool: 640 x 96 at launch; 128 x (96 - 40) freed >= 512 x (104 - 96) claimed (112 would deadlock)
     const int q = warp & 3;                          // TMEM lane quarter this warp may touch
     const int ew = warp - 4;
     const int part = ew >> 2;
@@ -969,6 +1056,69 @@ int avj_gemm_umma(int layout, const void* A, const void* B, void* C, int M, int 
     const int grid = units < sms ? units : sms;
     avj_launch_pdl(p.tma_store ? kerns_ts[0][wide][epi] : kerns[0][wide][epi], dim3(grid), dim3(threads), UG_SMEM_BYTES, s, ma, mb, mc, mp, p);
   }
+  AVJ_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// im2col-free patch embedding: out[row, :] = W[D, kd] . patch(token(row)) + bias + pos[token]   (fp32, tf32 tensor cores)
+// ------------------------------------------------------------------------------------------
+// Replaces the Conv3d / Conv2d projections of the reference (src/models/utils/patch_embed.py:85-102) for the tokens a
+// mask keeps (or all of them): no [tokens, kd] patch matrix is ever materialised, the producer warps of
+// gemm_umma_kernel<EPI_TRANSPOSED, 8, false, true> gather patch rows straight out of the clip into the operand tile.
+static int get_tensor_map_f32_2d(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer,
+                                 CUtensorMap* out) {
+  PFN_encodeTiled enc = get_encode_fn();
+  AVJ_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 4};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AVJ_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(fp32 weight) failed (%d)", (int)r);
+  return 0;
+}
+
+bool avj_patch_embed_umma_supported(int patch, int H, int W, int T, int tub, int D) {
+  return patch == 16 && H % 16 == 0 && W % 16 == 0 && T % tub == 0 && tub >= 1 && pick_block_n(D) != 0;
+}
+
+int avj_patch_embed_umma(const float* x, const int64_t* idx, const float* w, float* out, int B, int C, int T, int H, int W, int tub,
+                         int patch, int Kt, int D, int ldc, const avj_epilogue& ep, cudaStream_t s) {
+  AVJ_CHECK(avj_patch_embed_umma_supported(patch, H, W, T, tub, D), "avj_patch_embed: unsupported geometry (patch %d, %dx%d, D %d)", patch, H, W, D);
+  AVJ_CHECK(ep.out_dtype == AVJ_F32 && !ep.act && !ep.dact_aux && !ep.accumulate && !ep.residual, "avj_patch_embed: fp32 output with bias / positional rows only");
+  AVJ_CHECK(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15) == 0, "avj_patch_embed: x and w must be 16-byte aligned");
+  const int n_w = W / 16, n_h = H / 16, n_full = (T / tub) * n_h * n_w;
+  const int kd = C * tub * 256;
+  AVJ_CHECK(idx != nullptr || Kt == n_full, "avj_patch_embed: without a token list every token is embedded (Kt must be %d)", n_full);
+  const int M = B * Kt;
+  if (M == 0) return 0;
+  UmmaParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = D; p.K = kd; p.ldc = ldc; p.C = out; p.ep = ep;
+  p.k_blocks = kd / 32;
+  p.block_n = pick_block_n(D);
+  p.tiles_m = (M + UG_BM - 1) / UG_BM;
+  p.tiles_n = D / p.block_n;
+  p.split_k = 1;
+  p.kb_per_split = p.k_blocks;
+  p.ic_x = x; p.ic_idx = idx; p.ic_kt = Kt; p.ic_nw = n_w; p.ic_nh = n_h; p.ic_tub = tub; p.ic_c = C; p.ic_t = T;
+  AVJ_CHECK((int64_t)B * C * T * H * W < (int64_t)1 << 31, "avj_patch_embed: input larger than 2^31 elements");
+
+  CUtensorMap ma, mb, mc, mp;
+  memset(&ma, 0, sizeof(ma)); memset(&mc, 0, sizeof(mc)); memset(&mp, 0, sizeof(mp));
+  int rc = get_tensor_map_f32_2d(w, (uint64_t)kd, (uint64_t)D, (uint64_t)kd, 32, (uint32_t)p.block_n, &mb);
+  if (rc) return rc;
+
+  auto kern = gemm_umma_kernel<EPI_TRANSPOSED, 8, false, true>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, UG_SMEM_BYTES); });
+  AVJ_CHECK(attr_err == cudaSuccess, "cudaFuncSetAttribute(patch-embed kernel) failed: %s", cudaGetErrorString(attr_err));
+  const int units = p.tiles_m * p.tiles_n;
+  const int sms = avj_num_sms();
+  avj_launch_pdl(kern, dim3(units < sms ? units : sms), dim3(128 + 32 * 8), UG_SMEM_BYTES, s, ma, mb, mc, mp, p);
   AVJ_LAUNCH_CHECK();
   return 0;
 }

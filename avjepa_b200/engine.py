@@ -16,6 +16,7 @@ Residual stream and its gradient are fp32; GEMM/attention operands are the compu
 (bf16 in production, fp32 in check mode).
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -106,6 +107,20 @@ def gemm(mode, layout, A, B_, Cp, M, N, K, lda, ldb, ldc, out_dtype, bias=None, 
                   int(out_dtype), out_map if out_map is not None else _cabi.IDENTITY)
     _cabi.call('avj_gemm', mode.code, layout, A, B_, Cp, int(M), int(N), int(K), int(lda), int(ldb), int(ldc),
                C.byref(ep), stream())
+
+
+def patch_embed_tma_enabled():
+    """AVJ_PATCH_EMBED_TMA=0: patch matrix (avj_patchify) + bf16 GEMM instead of the im2col-free tf32 kernel."""
+    return os.environ.get('AVJ_PATCH_EMBED_TMA', '1') != '0'
+
+
+def patch_embed(x, idx, w_f32, out, B, Cin, T, H, W, tub, patch, K, D, ldc, bias=None, pos=None, pos_idx=None, pos_rows=0,
+                out_map=None):
+    """Conv3d / Conv2d patch projection of the kept tokens straight out of the clip (avj_patch_embed)."""
+    ep = Epilogue(bias, None, pos, pos_idx, int(pos_rows), 0, None, None, 0, int(_cabi.F32),
+                  out_map if out_map is not None else _cabi.IDENTITY)
+    _cabi.call('avj_patch_embed', x, idx, w_f32, out, int(B), int(Cin), int(T), int(H), int(W), int(tub), int(patch), int(K),
+               int(D), int(ldc), C.byref(ep), stream())
 
 
 def layernorm_fwd(x, gamma, beta, y, y_dtype, mean, rstd, rows, D, eps):

@@ -88,6 +88,23 @@ int avj_gemm(int dtype, int layout, const void* A, const void* B, void* C,
 int avj_patchify(const float* x, const int64_t* idx, void* out, int out_dtype,
                  int B, int C, int T, int H, int W, int tub, int patch, int K, void* stream);
 
+/* ---- K1: the whole patch-embedding projection, im2col-free (src/models/utils/patch_embed.py:85-102:
+ *      `self.proj(x).flatten(2).transpose(1, 2)` of PatchEmbed3D / AudioVisionPatchEmbed3D.forward, then the
+ *      positional-embedding add of audiovision_transformer.py forward):
+ *        out[omap(b*K + j), :] = w[D, C*tub*256] . patch(x[b], token idx[b, j]) + ep->bias + ep->pos[idx[b, j], :]
+ *      x fp32 [B, C, T, H, W] (audio: C = 1, T = tub = 1), w the fp32 Conv weight viewed [D, C*tub*16*16], out fp32 with row
+ *      pitch ldc.  The patch rows (64-byte runs) are gathered by the producer warps with 16-byte cp.async copies straight out
+ *      of x into the swizzled operand tile, the weight tile arrives by TMA, and both are multiplied on the tensor cores
+ *      as tf32 (tcgen05.mma.kind::tf32); no patch matrix exists in HBM.  idx == NULL
+ *      embeds every token (K == tokens per clip).  Only ep->bias, ep->pos / pos_idx / pos_rows and ep->out_map are
+ *      honoured (out_dtype must be AVJ_F32).  patch must be 16 and D a multiple of 64; other geometries are an
+ *      error (callers use avj_patchify + avj_gemm there, as the fp32 check mode does). */
+int avj_patch_embed(const float* x, const int64_t* idx, const float* w, float* out,
+                    int B, int C, int T, int H, int W, int tub, int patch, int K, int D, int ldc,
+                    const avj_epilogue* ep, void* stream);
+/* 1 when avj_patch_embed accepts this geometry. */
+int avj_patch_embed_supported(int patch, int H, int W, int T, int tub, int D);
+
 /* ---- K3: apply_masks (src/masks/utils.py:14-34) for one mask, and its backward.
  *      out[b, j, :] = x[b, idx[b, j], :];  bwd: dx[b, idx[b, j], :] += dout[b, j, :]. */
 int avj_gather_rows_fwd(int dtype, const void* x, const int64_t* idx, void* out,

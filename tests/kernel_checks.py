@@ -216,6 +216,35 @@ def check_patchify(code, B=2, seed=0, audio=False):
     return (e < 1e-4 and e2 < 1e-4), max(e, e2)
 
 
+def check_patch_embed(B=3, D=192, seed=0, audio=False, masked=True):
+    """avj_patch_embed (im2col-free, tf32 tensor cores) against Conv3d + bias + positional rows in fp32; rows land in a
+    wider sequence through the output row map like the encoder's [video | audio] layout."""
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    if audio:
+        x = torch.randn((B, 1, 1, 128, 192), generator=g, device=DEV)
+        Cc, T, H, W, tub, ntok = 1, 1, 128, 192, 1, 96
+    else:
+        x = torch.randn((B, 3, 16, 224, 224), generator=g, device=DEV)
+        Cc, T, H, W, tub, ntok = 3, 16, 224, 224, 2, 1568
+    w = torch.randn((D, Cc, tub, 16, 16), generator=g, device=DEV) * 0.05
+    bias = torch.randn(D, generator=g, device=DEV)
+    pos = torch.randn((ntok, D), generator=g, device=DEV)
+    K = 77 if masked else ntok
+    idx = torch.stack([torch.randperm(ntok, generator=g, device=DEV)[:K].sort().values for _ in range(B)]) if masked else None
+    N, off = K + 5, 3                                            # each sample's rows sit at [off, off + K) of N
+    out = torch.full((B * N, D), -7.0, device=DEV)
+    engine.patch_embed(x.data_ptr(), idx.data_ptr() if masked else None, w.data_ptr(), out.data_ptr(), B, Cc, T, H, W, tub, 16, K, D, D,
+                       bias=bias.data_ptr(), pos=pos.data_ptr(), pos_idx=idx.data_ptr() if masked else None, pos_rows=ntok,
+                       out_map=RowMap(K, N, off))
+    conv = (torch.nn.functional.conv3d(x.double(), w.double(), bias.double(), stride=(tub, 16, 16)).flatten(2).transpose(1, 2)
+            + pos.double()).float()                                                                     # [B, ntok, D]
+    ref = torch.gather(conv, 1, idx.unsqueeze(-1).repeat(1, 1, D)) if masked else conv
+    got = out.view(B, N, D)
+    e = _rel(got[:, off:off + K], ref)
+    untouched = bool((got[:, :off] == -7.0).all()) and bool((got[:, off + K:] == -7.0).all())
+    return (e < 2e-3 and untouched), e
+
+
 def check_rows(seed=0):
     """copy_rows / colsum / fill_mask_tokens with non-trivial row maps."""
     g = torch.Generator(device=DEV).manual_seed(seed)

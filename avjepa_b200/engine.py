@@ -58,14 +58,61 @@ def require_cuda(t, what):
         raise _cabi.AvjError(f'{what}: expected a CUDA tensor (device={t.device}); avjepa_b200 has no CPU path')
 
 
+class _BufferPool(object):
+    """Free list of large device buffers, per (device, stream).  The activation arenas of a step are 1-11 GB and
+    their size changes with every mask draw; asked for afresh each time, the torch caching allocator ends up calling
+    cudaMalloc (a device synchronisation) inside steps.  Arenas therefore return their buffer here when they die
+    and a new arena takes the smallest free buffer that fits (stream-ordered reuse, like the caching allocator's own
+    rule for one stream); a new buffer is only allocated, 12 % larger than asked, when none fits."""
+
+    def __init__(self):
+        self.free = {}
+
+    def take(self, nbytes, device):
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+        lst = self.free.setdefault(key, [])
+        best = None
+        for i, b in enumerate(lst):
+            if nbytes <= b.numel() <= 2 * nbytes and (best is None or b.numel() < lst[best].numel()):
+                best = i
+        if best is not None:
+            return key, lst.pop(best)
+        return key, torch.empty(int(nbytes * 1.12) + (1 << 20), dtype=torch.uint8, device=device)
+
+    def give(self, key, buf):
+        lst = self.free.setdefault(key, [])
+        lst.append(buf)
+        if len(lst) > 8:                                   # keep the largest ones
+            lst.sort(key=lambda b: b.numel())
+            del lst[0]
+
+
+_POOL = _BufferPool()
+_POOL_MIN = 64 << 20
+_POOL_ON = os.environ.get('AVJ_ARENA_POOL', '1') != '0'     # 0: every arena is a fresh torch.empty
+
+
 class Arena(object):
     """Byte arena over one torch allocation; hands out raw device pointers."""
 
     def __init__(self, nbytes, device):
         self.nbytes = int(nbytes)
-        self.buf = torch.empty(max(self.nbytes, 256) + 256, dtype=torch.uint8, device=device)
+        need = max(self.nbytes, 256) + 256
+        self._pool_key = None
+        device = torch.device(device)
+        if _POOL_ON and need >= _POOL_MIN and device.type == 'cuda':
+            self._pool_key, self.buf = _POOL.take(need, device)
+        else:
+            self.buf = torch.empty(need, dtype=torch.uint8, device=device)
         self.base = _align(self.buf.data_ptr())
         self.off = 0
+
+    def __del__(self):
+        try:
+            if self._pool_key is not None and self.buf is not None:
+                _POOL.give(self._pool_key, self.buf)
+        except Exception:                                   # interpreter shutdown
+            pass
 
     def alloc(self, nbytes):
         p = self.base + self.off

@@ -523,10 +523,20 @@ def main():
             # to the host every step (sync=True -> float(loss)).
             from avjepa_b200.app.avjepa.prefetch import DevicePrefetcher
             feed = DevicePrefetcher(((host_clips, host_asgram, host_masks[first_set + i]) for i in range(K + W)), dev)
+        if not e2e:
+            # allocator steady state: the activation arenas grow with the largest sequence lengths seen so far (mask draws
+            # differ per step), and growing means cudaMalloc -- a device synchronisation that a long training run only
+            # sees in its first few hundred steps.  Two extra untimed steps with the largest context / predictor
+            # sequences of this loop's mask sets come before the W warm-up steps.
+            ctx_rows = [sum(lens[first_set + i][m][0] + lens[first_set + i][m][1] for m in range(2)) for i in range(K + W)]
+            all_rows = [sum(sum(lens[first_set + i][m]) for m in range(2)) for i in range(K + W)]
+            for j in {max(range(K + W), key=lambda i: ctx_rows[i]), max(range(K + W), key=lambda i: all_rows[i])}:
+                step(clips_d, asgram_d, *dev_masks[j], epoch=0, sync=False)
         for i in range(K + W):
             if i == W:
                 barrier()
                 launches = _cabi.launch_count()
+                mallocs = torch.cuda.memory_stats(dev).get('num_device_alloc', 0)
                 if step.grad_sync is not None:
                     step.grad_sync.exposed_ms()
                 ev0.record()
@@ -542,6 +552,10 @@ def main():
         exposed = step.grad_sync.exposed_ms() if step.grad_sync is not None else 0.0
         fl = sum(step_flops(args.model, lens[first_set + i]) for i in range(W, K + W)) / K
         last_loss = float(out[0])
+        mallocs = torch.cuda.memory_stats(dev).get('num_device_alloc', 0) - mallocs
+        if rank == 0:
+            print(f'[bench] {"e2e" if e2e else "resident"} loop: {ms:.2f} ms/step, {mallocs} cudaMalloc calls inside the timed region',
+                  file=sys.stderr, flush=True)
         return ms, fl, launches, last_loss, exposed
 
     sampler = ClockSampler(local)
@@ -609,6 +623,7 @@ def main():
         config=dict(workload=f'{args.model} AV-JEPA pretrain step (configs/pretrain/vitl16.yaml shape), batch {B}/GPU, '
                              f'16x224x224 video + 128x192 log-mel, 2 multiblock masks, predictor depth {PRED_DEPTH}',
                     parallelism=f'dp{world}', l2='inputs+weights (>1.5 GB/step) exceed the 126 MB L2; no explicit flush',
+                    prewarm='2 untimed steps with the largest mask draws before the W warm-up steps (activation arenas at steady-state size)',
                     masks='per-rank collator seeds (lengths differ across ranks)' if args.per_rank_masks else 'collator seeded with meta.seed on every rank, like the reference (same mask lengths on all ranks)',
                     clips_per_s_per_gpu=clips_per_s / world,
                     step_tflops_per_gpu=step_tflops, frac_of_bf16_peak=step_tflops / peaks['bf16_sustained'],

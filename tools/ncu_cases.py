@@ -26,6 +26,7 @@ CASES = {
     'gemm_square': lambda: kb.bench_gemm(GEMM_NT, 8192, 8192, 8192, 'none', 'square 8192'),
     'attn_target': lambda: kb.bench_attn(24, 1664, 16, 64, 'target enc'),
     'attn_pred': lambda: kb.bench_attn(24, 1216, 16, 24, 'predictor'),
+    'attn_pred_step': lambda: kb.bench_attn(24, 1304, 16, 24, 'predictor, the sequence length of the profiled bench step'),
     'ln': lambda: kb.bench_ln(R_T, 1024),
     'ln_ctx': lambda: kb.bench_ln(24 * 537, 1024),
     'ln_pred': lambda: kb.bench_ln(24 * 2450, 384),

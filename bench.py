@@ -152,7 +152,7 @@ def model_cfg(model, batch, fp32=False):
     return cfg
 
 
-def cpu_reference_rate(model, sample_batch, steps, warmup, budget_s=None):
+def cpu_reference_rate(model, sample_batch, steps, warmup, budget_s=None, full_batch=24):
     """The reference step on this host's cores: the live, unmodified reference modules (baseline/_ref, kind
     "reference") when installed, else the oracle port (kind "port").  fp32 -- CUDA autocast / GradScaler disable
     themselves without a GPU, exactly as in the reference.  Returns (cpu_baseline dict, median s/step, timed steps)."""
@@ -194,7 +194,7 @@ def cpu_reference_rate(model, sample_batch, steps, warmup, budget_s=None):
             break                      # bounded leg of the default bench run: at least 3 timed steps, then stop
     med = statistics.median(times)
     return dict(value=sample_batch / med, unit='clips/s', cores=cores, kind=kind, batch=sample_batch,
-                sample=f'{model} full step (fwd+bwd+AdamW+EMA) fp32, batch {sample_batch} (bounded sample of the batch-24 '
+                sample=f'{model} full step (fwd+bwd+AdamW+EMA) fp32, batch {sample_batch} (bounded sample of the batch-{full_batch} '
                        f'workload), {len(times)} timed steps after {min(warmup, i)} warm-up, median {med:.2f} s/step, {what}'), med, len(times)
 
 
@@ -203,7 +203,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     model = args.model
-    base, med, done = cpu_reference_rate(model, args.cpu_sample_batch, args.steps, args.warmup)
+    base, med, done = cpu_reference_rate(model, args.cpu_sample_batch, args.steps, args.warmup, full_batch=args.batch)
     line = dict(metric='clips/sec/GPU, ViT-L/16 AV-JEPA step', value=base['value'], unit='clips/s', n_gpus=args.gpus,
                 steps=done, warmup=args.warmup, ms_per_step=med * 1000.0, higher_is_better=True, scaling='weak',
                 vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
@@ -611,7 +611,7 @@ def main():
                 wl = ref_gpu.get('with_loggers', {}).get('clips_per_s')
                 ref_gpu['speedup_vs_with_loggers'] = (B / (ms_e2e * 1e-3)) / wl if wl else None
         if not args.no_cpu_baseline:
-            cpu, _, _ = cpu_reference_rate(args.model, args.cpu_sample_batch, 3, 1, budget_s=150.0)
+            cpu, _, _ = cpu_reference_rate(args.model, args.cpu_sample_batch, 3, 1, budget_s=150.0, full_batch=B)
 
     clips_per_s = world * B / (ms_res * 1e-3)
     e2e_clips = world * B / (ms_e2e * 1e-3)

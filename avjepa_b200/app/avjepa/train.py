@@ -60,6 +60,7 @@ class TrainStep(object):
         self.param_stats = DeviceParamStats()
         self.keep_zh, self.last_zh = False, None
         self.stats = None
+        self.pipeline_optimizer = os.environ.get('AVJ_DDP_PIPELINE_OPT', '1') != '0'
         # AVJ_TARGET_STREAM=1: target encoder on a second stream beside the context / predictor forward.  Measured neutral
         # (213.9 vs 213.9 clips/s, ViT-L B=24: the persistent GEMMs of either stream already fill the machine), so the
         # default keeps the reference's order on one stream.
@@ -124,7 +125,7 @@ class TrainStep(object):
             self.last_zh = ([t.detach() for t in z], h)
         return loss, loss_jepa, loss_reg
 
-    def backward_and_reduce(self, loss, n_masks=2):
+    def backward_and_reduce(self, loss, n_masks=2, defer=False):
         """Backward, then (data parallel) the SUM all-reduce of the flat gradient buffers -- overlapped with the
         backward when the GradSync supports it.  Returns the factor still owed to the gradients (1/world when the
         fused optimizer folds the averaging into its gradient multiplier, else 1.0).  bf16 needs no loss scaling
@@ -139,6 +140,8 @@ class TrainStep(object):
         loss.backward()
         if self.grad_sync is None:
             return 1.0
+        if defer and hasattr(self.grad_sync, 'can_pipeline') and self.grad_sync.can_pipeline(opt):
+            return None                  # the caller finishes with grad_sync.finish_pipelined (optimizer per reduced interval)
         return self.grad_sync.all_reduce(opt, average=not isinstance(opt, FusedAdamWEMA))
 
     def __call__(self, clips, asgram, masks_enc_v, masks_enc_a, masks_pred_v, masks_pred_a, epoch=0, sync=True,
@@ -158,10 +161,25 @@ class TrainStep(object):
         # waits for that copy (unless gradient norms / parameter statistics, which exist only after backward, were
         # asked for as well).
         early = self._stage(0, [loss, loss_jepa, loss_reg]) if sync else None
-        inv = self.backward_and_reduce(loss, n_masks=len(masks_enc_v))
+        # Without clipping and statistics nothing needs ALL gradients at once: every gradient interval can be updated as
+        # soon as its own all-reduce is done, under the all-reduces of the intervals behind it (AVJ_DDP_PIPELINE_OPT=0: off).
+        clipping = (epoch > self.warmup) and (self.clip_grad is not None)
+        defer = fused and not clipping and not log_stats and self.pipeline_optimizer
+        inv = self.backward_and_reduce(loss, n_masks=len(masks_enc_v), defer=defer)
         enc_norm = pred_norm = None
         coef = None
-        if fused and (epoch > self.warmup) and (self.clip_grad is not None):         # train.py:518-520
+        pipelined = inv is None
+        if pipelined:
+            m = next(self.momentum_scheduler)
+            inv = 1.0 / self.grad_sync.world_size
+            opt.begin_step()
+            for g, lo, hi in self.grad_sync.finish_pipelined(opt):
+                opt.step_interval(opt.range_of_grad(g), lo, hi, ema_momentum=m, inv_loss_scale=inv, zero_grads=True)
+            for r in opt._ranges:                                   # ranges without gradients (frozen tables): EMA copy only
+                if r['g'] is None:
+                    opt.step_interval(r, 0, r['flat'].numel(), ema_momentum=m, inv_loss_scale=inv, zero_grads=True)
+            opt.end_step(zero_grads=True)
+        elif fused and (epoch > self.warmup) and (self.clip_grad is not None):       # train.py:518-520
             enc_sq = opt.grad_norm_sq(lambda r: r['group'] in (0, 2))
             pred_sq = opt.grad_norm_sq(lambda r: r['group'] in (1, 3))
             ce, cp = torch.empty_like(enc_sq), torch.empty_like(pred_sq)
@@ -173,8 +191,11 @@ class TrainStep(object):
         elif (not fused) and (epoch > self.warmup) and (self.clip_grad is not None):
             enc_norm = torch.nn.utils.clip_grad_norm_(self.encoder.parameters(), self.clip_grad)
             pred_norm = torch.nn.utils.clip_grad_norm_(self.predictor.parameters(), self.clip_grad)
-        m = next(self.momentum_scheduler)
-        if fused:
+        if not pipelined:
+            m = next(self.momentum_scheduler)
+        if pipelined:
+            pass
+        elif fused:
             if log_stats:
                 self.param_stats.capture_grads(opt, coef, scale=inv)     # before the kernel below zeroes them
             opt.step(ema_momentum=m, coef_by_group=coef, inv_loss_scale=inv, zero_grads=True)

@@ -75,6 +75,12 @@ class GradSync(object):
             overlap = os.environ.get('AVJ_DDP_OVERLAP', '1') != '0'
         self.overlap = bool(overlap) and torch.cuda.is_available() and world_size > 1
         self.layers_per_bucket = layers_per_bucket
+        # AVJ_DDP_BF16=1: the overlapped all-reduces move bf16 copies of the gradient intervals (half the bytes on the
+        # wire and half the HBM / L2 traffic beside the backward); the fp32 flat buffer receives the widened sum.  Off by
+        # default: the sum is then rounded to 8 mantissa bits once per element (relative 2^-9), which the fp32 check
+        # mode's 1e-4 bar does not allow.
+        self.bf16_wire = os.environ.get('AVJ_DDP_BF16', '0') == '1'
+        self._wire = {}
         self._side = None
         self._events = None
         self._works = []
@@ -86,27 +92,32 @@ class GradSync(object):
         self.measure = False
         self._exposed = []
 
-    def _wait_all(self, works):
+    def _wait_all(self, works, new_step=True):
         if self.measure and torch.cuda.is_available():
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             for w in works:
                 w.wait()
             b.record()
-            self._exposed.append((a, b))
+            if new_step or not self._exposed:
+                self._exposed.append([])
+            self._exposed[-1].append((a, b))
         else:
             for w in works:
                 w.wait()
 
     def exposed_ms(self, reset=True):
         """Mean per-step time the compute stream spent blocked on gradient collectives since the last reset
-        (synchronises on the recorded events)."""
+        (synchronises on the recorded events; a step may wait several times, the waits are summed)."""
         if not self._exposed:
             return 0.0
         vals = []
-        for a, b in self._exposed:
-            b.synchronize()
-            vals.append(a.elapsed_time(b))
+        for pairs in self._exposed:
+            t = 0.0
+            for a, b in pairs:
+                b.synchronize()
+                t += a.elapsed_time(b)
+            vals.append(t)
         if reset:
             self._exposed = []
         return sum(vals) / len(vals)
@@ -144,6 +155,7 @@ class GradSync(object):
         self._opt, self._enc = optimizer, encoder_backbone
         self._left = {'encoder': int(n_encoder_backward), 'predictor': int(n_predictor_backward)}
         self._works = []
+        self._records = []
         self._done = {id(r['g']): [] for r in optimizer._ranges if r['g'] is not None}
         if self._side is None:
             self._side = torch.cuda.Stream()
@@ -170,10 +182,46 @@ class GradSync(object):
         done = self._done[id(g)]
         todo = self.pending_intervals(done, lo, hi)
         for a, b in todo:
+            works = []
             for c0 in range(a, b, self.bucket_elems):
                 c1 = min(b, c0 + self.bucket_elems)
-                self._works.append(tdist.all_reduce(g[c0:c1], op=tdist.ReduceOp.SUM, group=self.group, async_op=True))
+                if self.bf16_wire and g.is_cuda:
+                    works.append(self._reduce_bf16(g, c0, c1))
+                else:
+                    works.append(tdist.all_reduce(g[c0:c1], op=tdist.ReduceOp.SUM, group=self.group, async_op=True))
+            self._works += works
+            self._records.append((g, a, b, works))               # issue order == completion order on the NCCL stream
             done.append((a, b))
+
+    class _EventWork(object):
+        """work-like handle: wait() makes the current stream wait for an event."""
+
+        def __init__(self, ev):
+            self.ev = ev
+
+        def wait(self):
+            torch.cuda.current_stream().wait_event(self.ev)
+
+    def _reduce_bf16(self, g, c0, c1):
+        """g[c0:c1] <- widen(SUM over ranks of bf16(g[c0:c1])), on the stream that is current (the compute stream or the
+        side stream of the per-layer hooks); returns a handle whose wait() orders the caller behind the write-back."""
+        wire = self._wire.get(id(g))
+        if wire is None:
+            wire = torch.empty(g.numel(), dtype=torch.bfloat16, device=g.device)
+            self._wire[id(g)] = wire
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        cur = torch.cuda.current_stream()
+        if cur != self._side:                       # called from the compute stream: everything enqueued so far comes first
+            self._side.wait_stream(cur)
+        ev = torch.cuda.Event()
+        with torch.cuda.stream(self._side):
+            w = wire[c0:c1]
+            w.copy_(g[c0:c1])
+            tdist.all_reduce(w, op=tdist.ReduceOp.SUM, group=self.group, async_op=True).wait()
+            g[c0:c1].copy_(w)
+            ev.record(self._side)
+        return GradSync._EventWork(ev)
 
     def _ranges_of(self, kind):
         groups = (0, 2) if kind == 'encoder' else (1, 3)
@@ -224,6 +272,36 @@ class GradSync(object):
             for r in self._ranges_of(kind):                   # current stream: everything enqueued so far is ordered before
                 self._reduce(r['g'], 0, r['g'].numel())
 
+    def _check_coverage(self, flats):
+        for g in flats:                                       # every element exactly once
+            iv = sorted(self._done[id(g)])
+            assert iv and iv[0][0] == 0 and iv[-1][1] == g.numel() and all(a[1] == b[0] for a, b in zip(iv, iv[1:])), \
+                'gradient all-reduce coverage error'
+
+    def can_pipeline(self, optimizer):
+        """True when this step's backward ran with the overlap hooks armed for `optimizer` (finish_pipelined is legal)."""
+        return _ACTIVE is self and self._opt is optimizer and hasattr(optimizer, 'step_interval')
+
+    def finish_pipelined(self, optimizer):
+        """Generator over (flat gradient buffer, lo, hi) in the order the all-reduces were issued: each interval is yielded
+        once the compute stream has been made to wait for ITS collective only, so the caller can update that interval
+        (optimizer.step_interval) while later intervals are still being reduced.  Gradients are SUMS over ranks; the caller
+        owes the factor 1 / world_size.  Every element of every flat buffer is yielded exactly once."""
+        global _ACTIVE
+        assert self.can_pipeline(optimizer)
+        _ACTIVE = None
+        flats = optimizer.flat_grads()
+        for g in flats:                                       # the complement of what the hooks already started
+            self._reduce(g, 0, g.numel())
+        self._check_coverage(flats)
+        first = True
+        for g, a, b, works in self._records:
+            self._wait_all(works, new_step=first)
+            first = False
+            yield g, a, b
+        self._works = []
+        self._records = []
+
     # ------------------------------------------------------------------ entry point after backward
     def all_reduce(self, optimizer, average=True):
         global _ACTIVE
@@ -238,10 +316,8 @@ class GradSync(object):
             self._reduce(g, 0, g.numel())
         self._wait_all(self._works)
         self._works = []
-        for g in flats:                                       # every element exactly once
-            iv = sorted(self._done[id(g)])
-            assert iv and iv[0][0] == 0 and iv[-1][1] == g.numel() and all(a[1] == b[0] for a, b in zip(iv, iv[1:])), \
-                'gradient all-reduce coverage error'
+        self._records = []
+        self._check_coverage(flats)
         inv = 1.0 / self.world_size
         if not average:
             return inv

@@ -145,6 +145,7 @@ class FusedAdamWEMA(torch.optim.Optimizer):
         self._flat = True
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self._coef = torch.ones(1, dtype=torch.float32, device=dev)
+        self._coef_val = 1.0
         self._ws = torch.empty(int(_cabi.load().avj_sumsq_ws_floats(0)), dtype=torch.float32, device=dev)
 
     def _adopt_target_shadows(self, twins, klp, offs):
@@ -194,43 +195,71 @@ class FusedAdamWEMA(torch.optim.Optimizer):
         """One AdamW step on every group; EMA for paired ranges when `ema_momentum` is given.
         `coef_by_group`: optional {group index -> device float tensor} gradient multipliers
         (unscale x clip), else `inv_loss_scale` is applied.  `zero_grads`: clear the gradients in the same pass."""
+        self.begin_step()
+        for r in self._ranges:
+            self.step_interval(r, 0, r['flat'].numel(), ema_momentum=ema_momentum, inv_loss_scale=inv_loss_scale,
+                               coef_by_group=coef_by_group, zero_grads=zero_grads)
+        self.end_step(zero_grads)
+        return None
+
+    # The step in pieces: begin_step(); step_interval(range, lo, hi) for a partition of every range; end_step().
+    # The data-parallel step uses this to update each gradient interval as soon as ITS all-reduce has finished while the
+    # all-reduces of later intervals are still in flight (dist.GradSync.finish_pipelined).
+    def begin_step(self):
         self.ensure_built()
         self._step += 1
+
+    def range_of_grad(self, g):
         for r in self._ranges:
-            a = AdamWArgs()
-            a.p = r['flat'].data_ptr()
-            a.n = r['flat'].numel()
-            a.target = r['k'].data_ptr() if (r['k'] is not None and ema_momentum is not None) else None
-            a.target_lp = r['klp'].data_ptr() if (r['klp'] is not None and ema_momentum is not None) else None
-            a.ema_m = float(ema_momentum) if ema_momentum is not None else 1.0
-            if r['frozen']:
-                a.skip_update = 1
-                a.g = a.m = a.v = a.p_lp = None
-                a.lr = a.wd = 0.0
-                a.beta1, a.beta2, a.eps, a.step = 0.9, 0.999, 1e-8, self._step
-                if a.target is None:
-                    continue
-            else:
-                g = self.param_groups[r['group']]
-                a.g, a.m, a.v = r['g'].data_ptr(), r['m'].data_ptr(), r['v'].data_ptr()
-                a.p_lp = r['lp'].data_ptr()
-                a.lr, a.wd = float(g['lr']), float(g['weight_decay'])
-                a.beta1, a.beta2 = float(g['betas'][0]), float(g['betas'][1])
-                a.eps = float(g['eps'])
-                a.step = self._step
-                a.skip_update = 0
-                a.zero_grad = 1 if zero_grads else 0
-                if coef_by_group is not None and r['group'] in coef_by_group:
-                    a.scale_ptr = coef_by_group[r['group']].data_ptr()
-                elif inv_loss_scale != 1.0:
+            if r['g'] is g:
+                return r
+        raise KeyError('not a flat gradient buffer of this optimizer')
+
+    def step_interval(self, r, lo, hi, ema_momentum=None, inv_loss_scale=1.0, coef_by_group=None, zero_grads=False):
+        """AdamW (+ EMA, shadows, gradient zeroing) on elements [lo, hi) of range `r`; lo and hi are multiples of 8."""
+        n = int(hi) - int(lo)
+        if n <= 0:
+            return
+        o4, o2 = 4 * int(lo), 2 * int(lo)
+        a = AdamWArgs()
+        a.p = r['flat'].data_ptr() + o4
+        a.n = n
+        a.target = r['k'].data_ptr() + o4 if (r['k'] is not None and ema_momentum is not None) else None
+        a.target_lp = r['klp'].data_ptr() + o2 if (r['klp'] is not None and ema_momentum is not None) else None
+        a.ema_m = float(ema_momentum) if ema_momentum is not None else 1.0
+        if r['frozen']:
+            a.skip_update = 1
+            a.g = a.m = a.v = a.p_lp = None
+            a.lr = a.wd = 0.0
+            a.beta1, a.beta2, a.eps, a.step = 0.9, 0.999, 1e-8, self._step
+            if a.target is None:
+                return
+        else:
+            g = self.param_groups[r['group']]
+            a.g, a.m, a.v = r['g'].data_ptr() + o4, r['m'].data_ptr() + o4, r['v'].data_ptr() + o4
+            a.p_lp = r['lp'].data_ptr() + o2
+            a.lr, a.wd = float(g['lr']), float(g['weight_decay'])
+            a.beta1, a.beta2 = float(g['betas'][0]), float(g['betas'][1])
+            a.eps = float(g['eps'])
+            a.step = self._step
+            a.skip_update = 0
+            a.zero_grad = 1 if zero_grads else 0
+            if coef_by_group is not None and r['group'] in coef_by_group:
+                a.scale_ptr = coef_by_group[r['group']].data_ptr()
+            elif inv_loss_scale != 1.0:
+                if self._coef_val != inv_loss_scale:
                     self._coef.fill_(inv_loss_scale)
-                    a.scale_ptr = self._coef.data_ptr()
-                else:
-                    a.scale_ptr = None
-            _cabi.call('avj_adamw_ema_step', C.byref(a), engine.stream())
+                    self._coef_val = inv_loss_scale
+                a.scale_ptr = self._coef.data_ptr()
+            else:
+                a.scale_ptr = None
+        _cabi.call('avj_adamw_ema_step', C.byref(a), engine.stream())
+
+    _coef_val = None
+
+    def end_step(self, zero_grads=False):
         self._step_t += 1
         self._clean_at = engine.grad_touch_count() if zero_grads else -1
-        return None
 
     def scale_grads(self, factor):
         """Multiply every flat gradient buffer by `factor` (GradScaler.unscale_ semantics for a scale != 1)."""

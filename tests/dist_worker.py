@@ -51,9 +51,10 @@ def main():
         loss_full, _, _ = ref_step.forward_loss(clips.to(dev), asgram.to(dev), full['ev'], full['ea'], full['pv'], full['pa'])
         loss_full.backward()
         ref = [gf.clone() for gf in ref_step.optimizer.flat_grads()]
-        for overlap in (False, True):
+        for overlap in ((False, True, 'bf16') if mixed else (False, True)):
             enc, pred = build_product(model, seed=0, device=dev, pred_depth=2)
-            sync = GradSync(world, overlap=overlap, layers_per_bucket=3)
+            sync = GradSync(world, overlap=bool(overlap), layers_per_bucket=3)
+            sync.bf16_wire = overlap == 'bf16'             # gradient intervals cross the wire as bf16 (AVJ_DDP_BF16=1)
             step = S.make_train_step(enc, pred, mixed, grad_sync=sync)
             loss, _, _ = step.forward_loss(clips[rows].to(dev), asgram[rows].to(dev), loc['ev'], loc['ea'], loc['pv'], loc['pa'])
             inv = step.backward_and_reduce(loss)
@@ -74,6 +75,23 @@ def main():
             w0 = w.clone()
             tdist.broadcast(w0, 0)
             ok = ok and bool(torch.equal(w, w0)) and out[0] == out[0]
+        # the pipelined finish (optimizer per reduced gradient interval, under the later all-reduces) must leave exactly the
+        # state the all-at-once finish leaves: same kernels on the same values, only launched per interval
+        states = []
+        for pipe in (True, False):
+            enc, pred = build_product(model, seed=0, device=dev, pred_depth=2)
+            step = S.make_train_step(enc, pred, mixed, grad_sync=GradSync(world, overlap=True, layers_per_bucket=3))
+            step.pipeline_optimizer = pipe
+            for _ in range(2):
+                step(clips[rows].to(dev), asgram[rows].to(dev), loc['ev'], loc['ea'], loc['pv'], loc['pa'])
+            states.append([p.detach().clone() for m in (step.encoder, step.predictor, step.target_encoder) for p in m.parameters()])
+        num = sum(float(((a.double() - b.double()) ** 2).sum()) for a, b in zip(*states))
+        den = sum(float((b.double() ** 2).sum()) for b in states[1])
+        perr = (num / den) ** 0.5
+        same = all(torch.equal(a, b) for a, b in zip(*states))
+        if rank == 0:
+            print(json.dumps(dict(world=world, model=model, mixed=mixed, pipelined_optimizer_vs_plain_rel_err=perr, bit_identical=same)), flush=True)
+        ok = ok and (same if not mixed else perr < 1e-4)
     tdist.barrier()
     tdist.destroy_process_group()
     if not ok:

@@ -43,6 +43,7 @@ struct UmmaParams {
   uint32_t mn_lbo, mn_sbo, mn_kadv;   // MN-major descriptor fields / k-advance (16 B units)
   void* C;
   int tma_store;         // thread==row epilogues: bf16 C (and pre_out) leave through smem + TMA bulk stores
+  int gelu_exact;        // AVJ_GELU_EXACT=1: erff() GELU / GELU' (generic epilogue) instead of the fitted sigmoid form
   // ---- im2col-free patch embedding (gemm_umma_kernel<..., IM2COL = true> only): A rows are tokens whose 16 x 16 patch
   //      rows are gathered straight out of the clip / spectrogram into the operand tile; both operands are fp32 in
   //      shared memory and the MMA is kind::tf32 (k-block = 32 elements = two patch rows of one (channel, frame))
@@ -323,7 +324,8 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, const CUtenso
 #pragma unroll
           for (int i = 0; i < 32; i += 4) atomicAdd(reinterpret_cast<float4*>(out + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
         } else {
-          epilogue_apply_store<bf16, 32, true>(ep, p.C, p.ldc, p.N, row, n0, v, add);
+          if (p.gelu_exact) epilogue_apply_store<bf16, 32, false>(ep, p.C, p.ldc, p.N, row, n0, v, add);
+          else epilogue_apply_store<bf16, 32, true>(ep, p.C, p.ldc, p.N, row, n0, v, add);
         }
       }
     }
@@ -988,7 +990,11 @@ int avj_gemm_umma(int layout, const void* A, const void* B, void* C, int M, int 
   const bool adds = ep.residual || ep.pos || ep.accumulate;
   int epi;
   static const uint32_t force_generic = env_u32("AVJ_EPI_GENERIC", 0);
-  if (force_generic) epi = EPI_GENERIC;
+  // AVJ_GELU_EXACT=1 (A/B aid): bf16 GEMMs evaluate GELU / GELU' with erff() like the fp32 check mode; those launches
+  // take the run-time-dispatched epilogue
+  static const uint32_t gelu_exact = env_u32("AVJ_GELU_EXACT", 0);
+  p.gelu_exact = (gelu_exact && (ep.act || ep.dact_aux)) ? 1 : 0;
+  if (force_generic || p.gelu_exact) epi = EPI_GENERIC;
   else if (ep.out_dtype == AVJ_F32) epi = (ep.act || ep.dact_aux) ? EPI_GENERIC : EPI_TRANSPOSED;
   else if (adds || p.split_k > 1 || (ep.act && ep.dact_aux)) epi = EPI_GENERIC;
   else if (ep.act) epi = EPI_GELU;

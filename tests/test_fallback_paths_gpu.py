@@ -33,6 +33,8 @@ ENVS = [
     dict(AVJ_ATTN_TMEM_P='0', AVJ_ATTN_BWD_MW='1', AVJ_GEMM_TMA_STORE='0', AVJ_GEMM_EW16='0'),
     dict(AVJ_ATTN_TMA='0', AVJ_GEMM_2CTA='0', AVJ_PDL='0'),
     dict(AVJ_ATTN_POLY='1', AVJ_ATTN_BWD_MW='1', AVJ_GEMM_EW16='0'),
+    dict(AVJ_GELU_EXACT='1', AVJ_ATTN_ILV='0', AVJ_ATTN_BWD_SP='0', AVJ_ATTN_POLY='0'),
+    dict(AVJ_ATTN_BWD_PP='1', AVJ_GEMM_SPLITK_OLD='1'),
 ]
 
 

@@ -282,9 +282,17 @@ def build_training(args, device, world_size=1, rank=0, ipe=None):
         use_sdpa=meta.get('use_sdpa', False),
     )
     target_encoder = copy.deepcopy(encoder)
-    collator = AVMB3DMaskCollator(
-        crop_size=data.get('crop_size', 224), num_frames=data.get('num_frames'), patch_size=data.get('patch_size'),
-        tubelet_size=data.get('tubelet_size'), cfgs_mask=mask_cfg)
+    if meta.get('device_masks', False) and torch.device(device).type == 'cuda':
+        # meta.device_masks: block positions drawn and index sets built on the GPU from a replica of torch's CPU generator
+        # (bit-identical masks, no mask H2D copies); one call ahead on a side stream
+        from avjepa_b200.src.masks.device_collator import DeviceAVMaskCollator
+        collator = DeviceAVMaskCollator(
+            crop_size=data.get('crop_size', 224), num_frames=data.get('num_frames'), patch_size=data.get('patch_size'),
+            tubelet_size=data.get('tubelet_size'), cfgs_mask=mask_cfg, device=device, prefetch=True)
+    else:
+        collator = AVMB3DMaskCollator(
+            crop_size=data.get('crop_size', 224), num_frames=data.get('num_frames'), patch_size=data.get('patch_size'),
+            tubelet_size=data.get('tubelet_size'), cfgs_mask=mask_cfg)
     ipe = ipe or opt_cfg.get('ipe') or 300
     num_epochs, ipe_scale = opt_cfg.get('epochs'), opt_cfg.get('ipe_scale', 1.0)
     optimizer, scaler, scheduler, wd_scheduler = init_opt(

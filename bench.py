@@ -446,6 +446,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-parity', action='store_true', help='skip the B=2 oracle parity block')
     ap.add_argument('--no-reference-gpu', action='store_true', help='skip the reference-on-GPU competitor leg')
+    ap.add_argument('--device-masks', action='store_true',
+                    help='e2e loop: masks sampled on the GPU (DeviceAVMaskCollator, one call ahead) instead of copied from pinned host memory')
     ap.add_argument('--per-rank-masks', action='store_true',
                     help='N>1: every rank seeds its mask collator differently (lengths differ across ranks -> straggler skew). '
                          'Default: identical collator streams on all ranks, which is what the reference does -- it seeds every '
@@ -522,7 +524,14 @@ def main():
             # staged by the package's DevicePrefetcher (copy stream, one batch ahead); the loss is read back
             # to the host every step (sync=True -> float(loss)).
             from avjepa_b200.app.avjepa.prefetch import DevicePrefetcher
-            feed = DevicePrefetcher(((host_clips, host_asgram, host_masks[first_set + i]) for i in range(K + W)), dev)
+            feed = DevicePrefetcher(((host_clips, host_asgram, () if args.device_masks else host_masks[first_set + i])
+                                     for i in range(K + W)), dev)
+            dev_coll = None
+            if args.device_masks:
+                from avjepa_b200.src.masks.device_collator import DeviceAVMaskCollator
+                torch.manual_seed(234 + (rank if args.per_rank_masks else 0))
+                dev_coll = DeviceAVMaskCollator(MASK_CFG, crop_size=224, num_frames=16, patch_size=16, tubelet_size=2, device=dev,
+                                                prefetch=True)
         if not e2e:
             # allocator steady state: the activation arenas grow with the largest sequence lengths seen so far (mask draws
             # differ per step), and growing means cudaMalloc -- a device synchronisation that a long training run only
@@ -542,6 +551,12 @@ def main():
                 ev0.record()
             if e2e:
                 c, a, m = next(feed)
+                while dev_coll is not None:
+                    try:
+                        m = dev_coll.sample(B)
+                        break
+                    except TypeError:                             # the reference collator's one-element quirk: draw again
+                        continue
                 out = step(c, a, *m, epoch=0, sync=True)          # loss scalars read back to the host every step
             else:
                 out = step(clips_d, asgram_d, *dev_masks[i], epoch=0, sync=False)
@@ -615,7 +630,9 @@ def main():
 
     clips_per_s = world * B / (ms_res * 1e-3)
     e2e_clips = world * B / (ms_e2e * 1e-3)
-    h2d = host_clips.numel() * 4 + host_asgram.numel() * 4 + sum(m.numel() * 8 for grp in host_masks[0] for m in grp)
+    h2d = host_clips.numel() * 4 + host_asgram.numel() * 4
+    if not args.device_masks:
+        h2d += sum(m.numel() * 8 for grp in host_masks[0] for m in grp)
     line = dict(
         metric='clips/sec/GPU, ViT-L/16 AV-JEPA step', value=clips_per_s, unit='clips/s', n_gpus=world, steps=K, warmup=W,
         ms_per_step=ms_res, higher_is_better=True, scaling='weak', vs_baseline=None,
@@ -625,10 +642,12 @@ def main():
                     parallelism=f'dp{world}', l2='inputs+weights (>1.5 GB/step) exceed the 126 MB L2; no explicit flush',
                     prewarm='2 untimed steps with the largest mask draws before the W warm-up steps (activation arenas at steady-state size)',
                     masks='per-rank collator seeds (lengths differ across ranks)' if args.per_rank_masks else 'collator seeded with meta.seed on every rank, like the reference (same mask lengths on all ranks)',
+                    e2e_masks='sampled on the GPU (avj_mask_collate, bit-exact replica of the CPU generator)' if args.device_masks else 'pinned host tensors from the host collator',
                     clips_per_s_per_gpu=clips_per_s / world,
                     step_tflops_per_gpu=step_tflops, frac_of_bf16_peak=step_tflops / peaks['bf16_sustained'],
                     flops_per_clip=flops_clip, loss=loss_res),
-        e2e=dict(value=e2e_clips, unit='clips/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=12,
+        e2e=dict(value=e2e_clips, unit='clips/s', h2d_bytes_per_step=int(h2d),
+                 d2h_bytes_per_step=12 + (4 * (len(MASK_CFG) * B * 4 + 1) if args.device_masks else 0),
                  ms_per_step=ms_e2e, loss=loss_e2e),
         gpu_launches=int(round(launches * K)), gpu_launches_per_step=launches, clocks=clocks, roofline=roof, parity=parity,
         reference_gpu=ref_gpu, cpu_baseline=cpu)

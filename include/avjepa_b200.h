@@ -105,6 +105,20 @@ int avj_patch_embed(const float* x, const int64_t* idx, const float* w, float* o
 /* 1 when avj_patch_embed accepts this geometry. */
 int avj_patch_embed_supported(int patch, int H, int W, int T, int tub, int D);
 
+/* ---- device-side mask sampling (src/masks/avmultiblock3d.py:131-234, the per-sample loop of _AVMaskGenerator.__call__ for all
+ *      mask generators of one step): block origins are drawn on the GPU from rng_state, a replica of torch's CPU generator
+ *      (int32[626] in device memory = 624 MT19937 words, values left in the block, index of the next word; updated in place),
+ *      in the reference's draw order (video top, left, start, audio top, left per block; a sample whose video context comes out
+ *      empty is drawn again).  gens is a HOST array [n_gen][5] = {t, h, w, blocks per sample, max_context_duration} (the block
+ *      size of this step, drawn by the caller from the seeded per-step generator).  For generator g and sample b the ascending
+ *      kept video ids go to enc_v[g][b][0 .. counts[g][b][0]), kept audio ids to enc_a (counts[..][1]), dropped video / audio
+ *      ids to pred_v / pred_a (counts[..][2], [3]); rows are NV = duration*height*width (NA = a_height*a_width) wide.
+ *      status (zeroed by the caller): bit 0 = some index set has exactly one element (the reference raises TypeError there),
+ *      bit 1 = gave up resampling.  One single-CTA launch. */
+int avj_mask_collate(void* rng_state, const int32_t* gens, int n_gen, int B, int duration, int height, int width,
+                     int a_height, int a_width, int a_block_h, int a_block_w, int64_t* enc_v, int64_t* pred_v,
+                     int64_t* enc_a, int64_t* pred_a, int32_t* counts, int32_t* status, void* stream);
+
 /* ---- K3: apply_masks (src/masks/utils.py:14-34) for one mask, and its backward.
  *      out[b, j, :] = x[b, idx[b, j], :];  bwd: dx[b, idx[b, j], :] += dout[b, j, :]. */
 int avj_gather_rows_fwd(int dtype, const void* x, const int64_t* idx, void* out,

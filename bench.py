@@ -532,7 +532,7 @@ def main():
                 torch.manual_seed(234 + (rank if args.per_rank_masks else 0))
                 dev_coll = DeviceAVMaskCollator(MASK_CFG, crop_size=224, num_frames=16, patch_size=16, tubelet_size=2, device=dev,
                                                 prefetch=True)
-        if not e2e:
+        if not e2e and not args.profile_only:
             # allocator steady state: the activation arenas grow with the largest sequence lengths seen so far (mask draws
             # differ per step), and growing means cudaMalloc -- a device synchronisation that a long training run only
             # sees in its first few hundred steps.  Two extra untimed steps with the largest context / predictor

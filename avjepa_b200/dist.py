@@ -203,8 +203,9 @@ class GradSync(object):
             torch.cuda.current_stream().wait_event(self.ev)
 
     def _reduce_bf16(self, g, c0, c1):
-        """g[c0:c1] <- widen(SUM over ranks of bf16(g[c0:c1])), on the stream that is current (the compute stream or the
-        side stream of the per-layer hooks); returns a handle whose wait() orders the caller behind the write-back."""
+        """g[c0:c1] <- widen(SUM over ranks of bf16(g[c0:c1])): narrowing copy, all-reduce and widening copy run on the side
+        stream (behind everything the calling stream has enqueued); returns a handle whose wait() orders the caller behind
+        the write-back."""
         wire = self._wire.get(id(g))
         if wire is None:
             wire = torch.empty(g.numel(), dtype=torch.bfloat16, device=g.device)

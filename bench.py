@@ -539,7 +539,8 @@ def main():
             # sequences of this loop's mask sets come before the W warm-up steps.
             ctx_rows = [sum(lens[first_set + i][m][0] + lens[first_set + i][m][1] for m in range(2)) for i in range(K + W)]
             all_rows = [sum(sum(lens[first_set + i][m]) for m in range(2)) for i in range(K + W)]
-            for j in {max(range(K + W), key=lambda i: ctx_rows[i]), max(range(K + W), key=lambda i: all_rows[i])}:
+            # always exactly two steps: under --per-rank-masks the ranks pick different sets, and a step is a collective
+            for j in (max(range(K + W), key=lambda i: ctx_rows[i]), max(range(K + W), key=lambda i: all_rows[i])):
                 step(clips_d, asgram_d, *dev_masks[j], epoch=0, sync=False)
         for i in range(K + W):
             if i == W:

@@ -157,6 +157,23 @@ def bench_gather(B, N, K, D):
                           frac=round(gbs / PEAKS['hbm_gbs'], 3))), flush=True)
 
 
+def bench_patch_embed(B, D, K=None):
+    """im2col-free patch embedding of a [B, 3, 16, 224, 224] clip batch: every token (K None) or K kept tokens per clip."""
+    x = torch.randn((B, 3, 16, 224, 224), device=DEV)
+    w = torch.randn((D, 1536), device=DEV) * 0.02
+    bias = torch.randn(D, device=DEV)
+    pos = torch.randn((1568, D), device=DEV)
+    Kt = K or 1568
+    idx = torch.stack([torch.randperm(1568, device=DEV)[:Kt].sort().values for _ in range(B)]) if K else None
+    out = torch.empty((B * Kt, D), device=DEV)
+    ms = timeit(lambda: engine.patch_embed(x.data_ptr(), idx.data_ptr() if K else None, w.data_ptr(), out.data_ptr(), B, 3, 16, 224, 224, 2, 16,
+                                           Kt, D, D, bias=bias.data_ptr(), pos=pos.data_ptr(), pos_idx=idx.data_ptr() if K else None,
+                                           pos_rows=1568))
+    fl = 2.0 * B * Kt * D * 1536
+    print(json.dumps(dict(kernel='patch_embed (im2col-free, tf32)', B=B, tokens=B * Kt, D=D, ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1),
+                          clip_gbs=round(B * Kt * 1536 * 4 / (ms * 1e-3) / 1e9, 1))), flush=True)
+
+
 def bench_loss(rows, D):
     z = torch.randn((rows, D), device=DEV)
     h = torch.randn((rows, D), device=DEV)
@@ -204,6 +221,9 @@ if __name__ == '__main__':
         bench_attn(24, 1664, 16, 64, 'target enc')
         bench_attn(24, 384, 16, 64, 'ctx enc')
         bench_attn(24, 1216, 16, 24, 'predictor')
+    if which == 'patch':
+        bench_patch_embed(24, 1024)
+        bench_patch_embed(24, 1024, K=184)
     if which == 'attn_h':                               # ViT-H (config 4): 16 heads of 80
         bench_attn(24, 1664, 16, 80, 'vit_huge target enc')
         bench_attn(24, 384, 16, 80, 'vit_huge ctx enc')

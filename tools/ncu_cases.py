@@ -27,6 +27,7 @@ CASES = {
     'attn_target': lambda: kb.bench_attn(24, 1664, 16, 64, 'target enc'),
     'attn_pred': lambda: kb.bench_attn(24, 1216, 16, 24, 'predictor'),
     'attn_pred_step': lambda: kb.bench_attn(24, 1304, 16, 24, 'predictor, the sequence length of the profiled bench step'),
+    'patch_embed': lambda: kb.bench_patch_embed(24, 1024),
     'ln': lambda: kb.bench_ln(R_T, 1024),
     'ln_ctx': lambda: kb.bench_ln(24 * 537, 1024),
     'ln_pred': lambda: kb.bench_ln(24 * 2450, 384),

@@ -232,16 +232,18 @@ def reference_gpu_rate(model, batch, dev, host_clips, host_asgram, mask_sets, st
             tr = R.ReferenceTrainer(model_cfg(model, batch), dev, with_loggers=loggers)
             dm = [[[m.to(dev) for m in grp] for grp in s] for s in mask_sets[:steps + warmup]]
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            last = None
+            last = first = None
             for i in range(steps + warmup):
                 if i == warmup:
                     torch.cuda.synchronize()
                     e0.record()
                 last = tr.train_step(clips, asgram, *dm[i])
+                if first is None:
+                    first = last['loss']              # loss of the freshly initialised model on mask set 0
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / steps
-            out[tag] = dict(ms_per_step=ms, clips_per_s=batch / (ms * 1e-3), loss=last['loss'])
+            out[tag] = dict(ms_per_step=ms, clips_per_s=batch / (ms * 1e-3), loss=last['loss'], first_step_loss=first)
         except Exception as e:      # the competitor arm must never take the bench line down with it
             out[tag] = dict(error=f'{type(e).__name__}: {e}'[:300])
         finally:
@@ -508,6 +510,13 @@ def main():
     def to_device(s):
         return [[m.to(dev, non_blocking=True) for m in grp] for grp in s]
 
+    # full-size parity probe: the loss of the freshly initialised model on mask set 0 at the FULL batch; the reference-on-GPU
+    # leg below starts from the same seed (bit-identical initial weights) and reports the same quantity from its first step
+    loss_first = None
+    if world == 1 and not args.no_reference_gpu and not args.fp32 and not args.profile_only:
+        with torch.no_grad():
+            loss_first = float(step.forward_loss(host_clips.to(dev), host_asgram.to(dev), *to_device(host_masks[0]))[0])
+
     def barrier():
         if world > 1:
             tdist.barrier()
@@ -621,6 +630,13 @@ def main():
         torch.cuda.empty_cache()
         if not args.no_reference_gpu and not args.fp32:
             ref_gpu = reference_gpu_rate(args.model, B, dev, host_clips, host_asgram, mask_sets)
+            ref_first = ref_gpu.get('no_loggers', {}).get('first_step_loss')
+            if loss_first is not None and ref_first:
+                ref_gpu['full_size_parity'] = dict(
+                    batch=B, first_step_loss=loss_first, reference_first_step_loss=ref_first,
+                    rel=abs(loss_first - ref_first) / abs(ref_first), bar=1e-2,
+                    what='loss of the freshly initialised model (same seed: bit-identical weights) on the same clips and masks, '
+                         'this build (bf16) vs the unmodified reference under bf16 autocast on this GPU')
             ok = ref_gpu.get('no_loggers', {}).get('clips_per_s')
             if ok:
                 ref_gpu['speedup_vs_no_loggers'] = (B / (ms_e2e * 1e-3)) / ok

@@ -59,8 +59,11 @@ template <int HDP, bool KV> struct UbSmem {
   // HDP = 128: every tile is two 64-column SWIZZLE_128B halves (RHALF / CHALF apart), 161 KB -> one CTA per SM
   static constexpr uint32_t RHALF = 128 * UaTile<HDP>::PITCH, CHALF = 64 * UaTile<HDP>::PITCH;
   static constexpr uint32_t ROW_TILE = RHALF * UaTile<HDP>::NH, COL_TILE = CHALF * UaTile<HDP>::NH;
+  // single pass (HDP == 32 KV pass): TWO dS^T tiles back to back -- the dQ MMAs run once per PAIR of steps with M = 128
+  // (queries of both steps), reading both tiles as the two 64-query chunks of one MN-major operand
+  static constexpr uint32_t NDS = (KV && HDP == 32) ? 2 : 1;
   static constexpr uint32_t R1 = 0, R2 = ROW_TILE, C1 = 2 * ROW_TILE, C2 = C1 + NST * COL_TILE,
-                            DS = C2 + NST * COL_TILE, P = DS + UB_PD_TILE,
+                            DS = C2 + NST * COL_TILE, P = DS + NDS * UB_PD_TILE,
                             STAT = KV ? P + UB_PD_TILE : P,            // KV pass: [SB][lse2 64 | delta 64] floats
                             BARS = STAT + (KV ? SB * 512 : 0), TOTAL = BARS + 192;
 };
@@ -80,12 +83,13 @@ template <int HDP, bool KV> struct UbSmem {
 // group of tcgen05.mma (M = 64; A = the dS^T tile in shared memory read MN-major, B = the stationary K tile read MN-major),
 // its fp32 result leaves TMEM through a 64 x hd staging tile and ONE TMA reduce-add (cp.reduce.async.bulk.tensor .add)
 // into an fp32 dQ accumulator [B, N, H, hd]; dS^T therefore lives in shared memory (it feeds dK K-major and dQ MN-major),
-// P^T stays in tensor memory.  TMEM: S^T 64 | dP^T 64 | dV 32 | dK 32 | P^T 32 | dQ 32 = 256 columns.
+// P^T stays in tensor memory.  TMEM: S^T 64 | dP^T 64 | dV 32 | dK 32 | P^T 32 | dQ 32 = 256 columns.  The dQ MMAs and the
+// reduce-add run once per PAIR of steps (M = 128: two dS^T tiles kept side by side), so a pair costs 32 instead of 40 MMAs.
 template <int HDP, bool TMA, bool KV, int MW, bool TS, bool PP, bool SP>
 __global__ void __launch_bounds__(128 + 128 * MW, 2)
 fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_constant__ CUtensorMap map_qkv64,
                    const __grid_constant__ CUtensorMap map_do, const __grid_constant__ CUtensorMap map_dq,
-                   const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+                   const __grid_constant__ CUtensorMap map_dq2, const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                    const float* __restrict__ lse2, const float* __restrict__ delta, bf16* __restrict__ dqkv,
                    int N, int n_pad, int H, int hd, float scale, float scale_log2, int dbg) {
   using L = UbSmem<HDP, KV>;
@@ -276,17 +280,23 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
             // three INDEPENDENT accumulation chains (dV: 4 MMAs, dK: 4, dQ tile: 8).  Small dependent MMAs are latency-, not
             // throughput-bound (ncu: tensor pipe 21 % busy while the math warps wait for these 16 MMAs), so the chains are
             // issued round-robin instead of one after the other.
+            // dQ once per PAIR of steps: M = 128 queries (even step = chunk 0 in sDS, odd step = chunk 1 in sDS + 16 KB, the
+            // chunk stride is the descriptor's leading-byte offset), 8 MMAs per pair instead of 8 per step -- the step is
+            // bound by the NUMBER of small MMAs (each occupies the tensor pipe ~67 cycles whatever its size).  A last
+            // unpaired step (T odd) keeps the M = 64 form on buffer 0.
+            const bool pair = (t & 1) != 0, tail = !pair && (t == T - 1);
             const uint32_t idesc_q = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(HDP >> 3) << 17) |
-                                     ((uint32_t)(64 >> 4) << 24);
-            const uint64_t dsm = ua_desc(sDS, 512, 64);      // MN-major view of dS^T: 64 queries contiguous, 16 keys per K step
+                                     ((uint32_t)((pair ? 128 : 64) >> 4) << 24);
+            const uint64_t dsm = ua_desc(sDS, UB_PD_TILE >> 4, 64);   // MN-major view of dS^T: 64 queries contiguous per chunk, 16 keys per K step
+            const uint64_t dsk = ua_desc(sDS + (t & 1) * UB_PD_TILE, 1, 64);   // K-major view of THIS step's tile (dK)
             const uint64_t r1m = TL::mnmajor(sR1);           // K tile: 16 keys per K step, hd contiguous
 #pragma unroll
             for (int k = 0; k < UB_BN / 16; ++k) {
               const uint32_t acc = (t > 0 || k > 0) ? 1u : 0u;
-              ua_mma(tmem + DQ_COL, dsm + 128 * (2 * k), r1m + TL::MN_KADV * (2 * k), idesc_q, k > 0 ? 1u : 0u);
+              if (pair || tail) ua_mma(tmem + DQ_COL, dsm + 128 * (2 * k), r1m + TL::MN_KADV * (2 * k), idesc_q, k > 0 ? 1u : 0u);
               ua_mma_ts(tmem + O1_COL, tmem + PT_COL + 8 * k, c2m + TL::MN_KADV * k, idesc_o, acc);           // dV += P^T dO
-              ua_mma(tmem + DQ_COL, dsm + 128 * (2 * k + 1), r1m + TL::MN_KADV * (2 * k + 1), idesc_q, 1u);
-              ua_mma(tmem + O2_COL, dsd + 2 * k, c1m + TL::MN_KADV * k, idesc_o, acc);                        // dK += dS^T Q
+              if (pair || tail) ua_mma(tmem + DQ_COL, dsm + 128 * (2 * k + 1), r1m + TL::MN_KADV * (2 * k + 1), idesc_q, 1u);
+              ua_mma(tmem + O2_COL, dsk + 2 * k, c1m + TL::MN_KADV * k, idesc_o, acc);                        // dK += dS^T Q
             }
           } else {
 #pragma unroll
@@ -380,7 +390,7 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
     // [16 wg, 16 wg + 16) of rows [16 q, 16 q + 16).  The staging tile is known to be free: the issuing thread waited for the
     // previous reduce to have READ it before this step's statistics barrier (bar.sync 1), which every math thread has passed.
     const bool dq_issuer = (threadIdx.x == 128);
-    auto flush_dq = [&](int tq) {
+    auto flush_dq = [&](int tq, bool pair) {       // pair: 128 queries (tiles tq, tq + 1), TMEM row == lane; else 64 (M = 64 layout)
       uint32_t v[16];
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -388,8 +398,8 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
             "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
           : "r"(t_1 + DQ_COL + 16 * wg) : "memory");
       ua_ld_wait();
-      if (lane < 16) {
-        const uint32_t dst = sP + (uint32_t)((16 * q + lane) * hd + 16 * wg) * 4u;
+      if (pair || lane < 16) {
+        const uint32_t dst = sP + (uint32_t)((pair ? 32 * q + lane : 16 * q + lane) * hd + 16 * wg) * 4u;
 #pragma unroll
         for (int c = 0; c < 16; c += 4)
           if (16 * wg + c < hd)
@@ -399,7 +409,7 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
       asm volatile("bar.sync 3, %0;" ::"n"(128 * MW) : "memory");
       if (dq_issuer && !(dbg & 1)) {
         asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
-                     ::"l"(&map_dq), "r"(sP), "r"(h * hd), "r"(tq * UB_BN), "r"(b) : "memory");
+                     ::"l"(pair ? &map_dq2 : &map_dq), "r"(sP), "r"(h * hd), "r"(tq * UB_BN), "r"(b) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     };
@@ -458,13 +468,14 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
       }
       if (t > 0) ua_mbar_wait(o_done + bo, (t - 1) & 1);      // output MMAs of step t-1 done: P / dS smem is ours
       ua_fence_after();
-      if constexpr (SP) { if (t > 0 && !(dbg & 2)) flush_dq(t - 1); }        // dQ tile of step t-1: TMEM -> staging -> TMA reduce-add
+      // dQ of the pair of steps (t-2, t-1), complete since the MMAs of the odd step t-1: TMEM -> staging -> TMA reduce-add
+      if constexpr (SP) { if (t > 0 && ((t - 1) & 1) && !(dbg & 2)) flush_dq(t - 2, true); }
       if constexpr (SP) {
         // P^T -> tensor memory (A operand of dV), dS^T -> shared memory (A operand of dK, K-major, and of dQ, MN-major)
         ua_st_regs<CW / 2>(t_1 + PT_COL + col0 / 2, pk_p);
 #pragma unroll
         for (int c = 0; c < CW / 8; ++c) {
-          const uint32_t off = row * 128 + (((col0 / 8 + c) ^ (row & 7)) << 4);
+          const uint32_t off = (t & 1) * UB_PD_TILE + row * 128 + (((col0 / 8 + c) ^ (row & 7)) << 4);   // even / odd step buffer
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + off), "r"(pk_d[4 * c]), "r"(pk_d[4 * c + 1]),
                        "r"(pk_d[4 * c + 2]), "r"(pk_d[4 * c + 3]) : "memory");
         }
@@ -496,7 +507,8 @@ fa_bwd_umma_kernel(const __grid_constant__ CUtensorMap map_qkv128, const __grid_
     ua_mbar_wait(all_done, 0);
     ua_fence_after();
     if constexpr (SP) {
-      flush_dq(T - 1);
+      if (T & 1) flush_dq(T - 1, false);             // unpaired last step
+      else flush_dq(T - 2, true);
       if (dq_issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     // dqkv row layout [3][H][hd]: slot 0 = dQ, 1 = dK, 2 = dV
@@ -554,7 +566,8 @@ static int ub_dbg() {     // AVJ_ATTN_BWD_DBG (timing experiments only; results 
 }
 
 template <int HDP, bool TMA, bool KV, int MW, bool TS, bool PP, bool SP = false>
-static int ub_launch(const CUtensorMap& m128, const CUtensorMap& m64, const CUtensorMap& mdo, const CUtensorMap& mdq, const bf16* qkv, const bf16* dout,
+static int ub_launch(const CUtensorMap& m128, const CUtensorMap& m64, const CUtensorMap& mdo, const CUtensorMap& mdq, const CUtensorMap& mdq2,
+                     const bf16* qkv, const bf16* dout,
                      const float* lse2, const float* delta, bf16* dqkv, int B, int N, int n_pad, int H, int hd, float scale,
                      cudaStream_t s) {
   static bool set = false;
@@ -566,7 +579,7 @@ static int ub_launch(const CUtensorMap& m128, const CUtensorMap& m64, const CUte
     set = true;
   }
   dim3 grid((N + UB_BM - 1) / UB_BM, H, B);
-  avj_launch_pdl(fa_bwd_umma_kernel<HDP, TMA, KV, MW, TS, PP, SP>, grid, dim3(128 + 128 * MW), (size_t)smem, s, m128, m64, mdo, mdq, qkv, dout, lse2, delta, dqkv, N, n_pad,
+  avj_launch_pdl(fa_bwd_umma_kernel<HDP, TMA, KV, MW, TS, PP, SP>, grid, dim3(128 + 128 * MW), (size_t)smem, s, m128, m64, mdo, mdq, mdq2, qkv, dout, lse2, delta, dqkv, N, n_pad,
                  H, hd, scale, scale * 1.4426950408889634f, ub_dbg());
   AVJ_LAUNCH_CHECK();
   return 0;
@@ -585,9 +598,9 @@ static int ub_both(const bf16* qkv, const bf16* dout, const float* lse2, const f
     if ((rc = ua_make_map3d(dout, B, N, H * hd, 64, &mdo64, BC))) return rc;
     if ((rc = ua_make_map3d(dout, B, N, H * hd, 128, &mdo128, BC))) return rc;
   }
-  int rc = ub_launch<HDP, TMA, true, MW, TS, PP>(m128, m64, mdo64, m128, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
+  int rc = ub_launch<HDP, TMA, true, MW, TS, PP>(m128, m64, mdo64, m128, m128, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
   if (rc) return rc;
-  return ub_launch<HDP, TMA, false, MW, TS, PP>(m128, m64, mdo128, m128, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
+  return ub_launch<HDP, TMA, false, MW, TS, PP>(m128, m64, mdo128, m128, m128, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
 }
 
 // fp32 [B, N, cols] viewed as {cols, N, B}; box = {box_cols, box_rows, 1}, no swizzle (TMA reduce-add target of the dQ tiles)
@@ -618,14 +631,16 @@ int avj_copy_rows(const void* in, int in_dtype, int ld_in, avj_rowmap imap, void
 // single pass (head_dim <= 32, TMA): zero the fp32 dQ accumulator, ONE kernel for dK / dV / dQ, then dQ -> bf16 into dqkv[..., 0, :, :]
 static int ub_single(const bf16* qkv, const bf16* dout, const float* lse2, const float* delta, bf16* dqkv, float* dq_acc,
                      int B, int N, int n_pad, int H, int hd, float scale, cudaStream_t s) {
-  CUtensorMap m128, m64, mdo64, mdq;
+  CUtensorMap m128, m64, mdo64, mdq, mdq2;
   memset(&m128, 0, sizeof(m128)); memset(&m64, 0, sizeof(m64)); memset(&mdo64, 0, sizeof(mdo64)); memset(&mdq, 0, sizeof(mdq));
+  memset(&mdq2, 0, sizeof(mdq2));
   int rc;
   if ((rc = ua_make_map3d(qkv, B, N, 3 * H * hd, 128, &m128, 32))) return rc;
   if ((rc = ua_make_map3d(qkv, B, N, 3 * H * hd, 64, &m64, 32))) return rc;
   if ((rc = ua_make_map3d(dout, B, N, H * hd, 64, &mdo64, 32))) return rc;
   if ((rc = ub_make_map3d_f32(dq_acc, B, N, H * hd, 64, hd, &mdq))) return rc;
-  rc = ub_launch<32, true, true, 2, true, false, true>(m128, m64, mdo64, mdq, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
+  if ((rc = ub_make_map3d_f32(dq_acc, B, N, H * hd, 128, hd, &mdq2))) return rc;     // pairs of query tiles
+  rc = ub_launch<32, true, true, 2, true, false, true>(m128, m64, mdo64, mdq, mdq2, qkv, dout, lse2, delta, dqkv, B, N, n_pad, H, hd, scale, s);
   if (rc) return rc;
   const avj_rowmap ident = {0, 0, 0};
   return avj_copy_rows(dq_acc, AVJ_F32, H * hd, ident, dqkv, AVJ_BF16, 3 * H * hd, ident, B * N, H * hd, 0, s);

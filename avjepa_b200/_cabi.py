@@ -87,6 +87,7 @@ PROTOTYPES = {
     'avj_patchify': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'avj_patch_embed': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(Epilogue), _vp]),
     'avj_patch_embed_supported': (_i, [_i, _i, _i, _i, _i, _i]),
+    'avj_patch_embed_wgrad': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'avj_mask_collate': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'avj_gather_rows_fwd': (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'avj_gather_rows_bwd': (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -9,6 +9,8 @@ gradients of tensor inputs.  Reference call sites restated here:
 * encoder   -- ``src/models/audiovision_transformer.py:186-239``, ``vision_transformer.py:162-201``
 * predictor -- ``src/models/audiovisionpredictor.py:202-301``, ``predictor.py:175-239``
 """
+import os
+
 import torch
 
 from avjepa_b200 import _cabi, engine
@@ -217,17 +219,23 @@ def encoder_backward(mod, st, douts):
             if K == 0 or conv is None or src is None:
                 continue
             gw, gb = engine.grad_ptr(conv.weight), engine.grad_ptr(conv.bias) if conv.bias is not None else None
-            if patches is None and gw is not None:
-                # the forward embedded the tokens straight out of the clip; the weight gradient's second operand (kept tokens
-                # only, 2 % of the clip at 90 % masking) is gathered here, where it is consumed
-                patches = _patchify(src, idx, B, K, tb, p, mode)
             kd = conv.weight[0].numel()
+            fused_wgrad = (patches is None and gw is not None and mode.code == _cabi.BF16
+                           and os.environ.get('AVJ_PATCH_WGRAD_GATHER', '1') != '0')     # 0: patch matrix of the kept tokens + GEMM
+            if patches is None and gw is not None and not fused_wgrad:
+                patches = _patchify(src, idx, B, K, tb, p, mode)
             rm = rowmap(K, N, off)
             if gb is not None:
                 engine.colsum(dx0_g, F32, D, rm, gb, B * K, D, ws)
             if gw is not None:
                 engine.copy_rows(dx0_g, F32, D, rm, dxc, cd, D, IDENTITY, B * K, D)
-                engine.gemm(mode, GEMM_TN, dxc, patches.data_ptr(), gw, D, kd, B * K, D, kd, kd, F32, accumulate=1)
+                if fused_wgrad:
+                    # the forward embedded the tokens straight out of the clip; so does the weight gradient: its second operand
+                    # is gathered (and narrowed to bf16) by the GEMM's producer warps, no patch matrix exists in either direction
+                    _, Cs, Ts, Hs, Ws = src.shape
+                    engine.patch_embed_wgrad(src.data_ptr(), _ptr(idx), dxc, gw, B, Cs, Ts, Hs, Ws, tb, p, K, D)
+                else:
+                    engine.gemm(mode, GEMM_TN, dxc, patches.data_ptr(), gw, D, kd, B * K, D, kd, kd, F32, accumulate=1)
     if sync is not None:
         sync.on_backward_done('encoder', mod)
 

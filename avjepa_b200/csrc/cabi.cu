@@ -165,6 +165,18 @@ bool avj_patch_embed_umma_supported(int patch, int H, int W, int T, int tub, int
 int avj_patch_embed_umma(const float* x, const int64_t* idx, const float* w, float* out, int B, int C, int T, int H, int W, int tub,
                          int patch, int Kt, int D, int ldc, const avj_epilogue& ep, cudaStream_t s);
 
+int avj_patch_embed_wgrad_umma(const float* x, const int64_t* idx, const void* dy, float* gw, int B, int C, int T, int H, int W, int tub,
+                               int patch, int Kt, int D, cudaStream_t s);
+
+extern "C" int avj_patch_embed_wgrad(const float* x, const int64_t* idx, const void* dy, float* gw,
+                                     int B, int C, int T, int H, int W, int tub, int patch, int K, int D, void* stream) {
+  if (B == 0 || K == 0) return 0;
+  const int kd = C * tub * patch * patch;
+  // profiled as a GEMM (TN, accumulate, fp32 out) of M = D, N = kd, K = B*K tokens
+  AvjProfScope prof(AVJ_FAM_GEMM, 2.0 * B * K * (double)D * kd, stream, 2 | 32 | 128, D, kd, B * K);
+  return avj_patch_embed_wgrad_umma(x, idx, dy, gw, B, C, T, H, W, tub, patch, K, D, as_stream(stream));
+}
+
 extern "C" int avj_patch_embed_supported(int patch, int H, int W, int T, int tub, int D) {
   return avj_patch_embed_umma_supported(patch, H, W, T, tub, D) ? 1 : 0;
 }

@@ -410,7 +410,9 @@ __device__ __forceinline__ void epilogue_tile(const UmmaParams& p, const CUtenso
 // EW = number of epilogue warps: 8 (two per TMEM lane quarter, half of the columns each) or 16 (four per
 // quarter, a quarter of the columns each) for the thread==row epilogues, which are latency- rather than
 // issue-bound and double their throughput with twice the warps in flight.
-template <int EPI, int EW, bool TS, bool IM2COL = false>
+// GATHER: 0 = both operands by TMA; 1 = im2col-free patch embedding (A rows gathered out of the clip, tf32); 2 = its weight
+// gradient (B rows = the same patch values, gathered and converted to bf16 by the producer warps, MN-major).
+template <int EPI, int EW, bool TS, int GATHER = 0>
 __global__ void __launch_bounds__(128 + 32 * EW, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_p, const UmmaParams p) {
@@ -427,6 +429,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const uint32_t tempty_bar = tfull_bar + 16;           // [2]
   const uint32_t tmem_slot = tempty_bar + 16;           // u32
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  constexpr bool IM2COL = GATHER == 1, WGRAD = GATHER == 2;
+  const uint32_t tok_tab = bars + 256;                  // WGRAD: [2][64] s32 element offsets of the k-block's tokens (extra 512 bytes)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_trigger();
@@ -434,7 +438,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
-    for (int i = 0; i < UG_STAGES; ++i) { mbar_init(full_bar + 8 * i, IM2COL ? 97 : 1); mbar_init(empty_bar + 8 * i, 1); }
+    for (int i = 0; i < UG_STAGES; ++i) { mbar_init(full_bar + 8 * i, GATHER ? 97 : 1); mbar_init(empty_bar + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + 8 * i, 1); mbar_init(tempty_bar + 8 * i, 32 * EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -453,8 +457,89 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (warp < 4) {
     // warpgroup 0 hands its registers to the epilogue warpgroups (the kernel is compiled for 168); the gather loop of
     // the im2col producer needs more than 40, so that instantiation keeps the launch allocation everywhere
-    if constexpr (!IM2COL) reg_dec<40>();
-    if (IM2COL && warp != 1) {
+    if constexpr (!GATHER) reg_dec<40>();
+    if (WGRAD && warp != 1) {
+      // ================= producer, patch-embedding weight gradient (warps 0, 2, 3: 96 threads) =================
+      // dW[D, kd] += dY^T[D, tokens] . X[tokens, kd]: the contraction runs over the kept tokens, 64 per k-block.  A = dY (bf16,
+      // row-major [tokens, D]) arrives by TMA as an MN-major tile like every weight gradient; B = the patch values X is
+      // never materialised: each producer thread reads 8 consecutive floats of a token's patch row out of the clip,
+      // converts them to bf16 and stores the 16-byte chunk into the MN-major SWIZZLE_128B tile ([token][64 kd values] per
+      // 8 KB chunk of 64 columns).  Token element offsets of the k-block come from a small shared-memory table.
+      const int pt = warp == 0 ? lane : (warp - 1) * 32 + lane;      // 0 .. 95
+      const int HW = p.ic_nh * 16 * p.ic_nw * 16, Wd = p.ic_nw * 16;
+      const int cpr = p.block_n / 8;                                  // 16-byte chunks per token row of the stage
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int tile = u / p.split_k, ks = u % p.split_k;
+        const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const uint32_t tab = tok_tab + (it & 1) * 256;
+          if (pt < 64) {
+            const int t = kb * 64 + pt;
+            int off = -1;                                               // past the last token: a zero row
+            if (t < p.K) {
+              const int b = t / p.ic_kt, jj = t % p.ic_kt;
+              const int tok = p.ic_idx ? (int)__ldg(p.ic_idx + (int64_t)b * p.ic_kt + jj) : jj;
+              const int wt = tok % p.ic_nw, hrow = tok / p.ic_nw;
+              off = ((b * p.ic_c) * p.ic_t + (hrow / p.ic_nh) * p.ic_tub) * HW + (hrow % p.ic_nh) * 16 * Wd + wt * 16;
+            }
+            asm volatile("st.shared.s32 [%0], %1;" ::"r"(tab + 4 * pt), "r"(off) : "memory");
+          }
+          asm volatile("bar.sync 1, 96;" ::: "memory");
+          const uint32_t fb = full_bar + 8 * stage;
+          const uint32_t sa = smem_a + stage * UG_A_STAGE_BYTES;
+          const uint32_t sb = smem_b + stage * UG_B_STAGE_BYTES;
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          if (pt == 0) {
+            mbar_expect_tx(fb, UG_A_STAGE_BYTES);
+            tma_load_2d(sa, &tma_a, fb, m_blk * UG_BM, kb * UG_BK);
+            tma_load_2d(sa + 8192, &tma_a, fb, m_blk * UG_BM + 64, kb * UG_BK);
+          }
+          // eight chunks per round: all sixteen 16-byte loads are in flight before the first conversion (the shared-memory
+          // stores below are ordered asm statements, loads scheduled between them would each expose a full L2 round trip)
+          const int* tabp = reinterpret_cast<const int*>(smem_raw + (tab - raw));
+          const int total = 64 * cpr;
+          const int cshift = 31 - __clz(cpr);                        // block_n is 64, 128 or 256: cpr is a power of two
+          for (int q0 = pt; q0 < total; q0 += 8 * 96) {
+            float4 f[8][2];
+            uint32_t dst[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int q = q0 + 96 * e;
+              f[e][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+              f[e][1] = f[e][0];
+              dst[e] = 0xffffffffu;
+              if (q < total) {
+                const int r = q >> cshift, j = q & (cpr - 1);          // token row of the k-block, 16-byte chunk of its row
+                const int kk = n_blk * p.block_n + j * 8;              // first of 8 consecutive kd indices: (plane, dh, dw0)
+                const int off = tabp[r];
+                dst[e] = sb + (uint32_t)(j >> 3) * 8192u + (uint32_t)r * 128u + (uint32_t)(((j & 7) ^ (r & 7)) << 4);
+                if (off >= 0) {
+                  const int plane = kk >> 8;
+                  const float4* src = reinterpret_cast<const float4*>(
+                      p.ic_x + off + ((plane / p.ic_tub) * p.ic_t + plane % p.ic_tub) * HW + ((kk >> 4) & 15) * Wd + (kk & 15));
+                  f[e][0] = __ldg(src);
+                  f[e][1] = __ldg(src + 1);
+                }
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              if (dst[e] == 0xffffffffu) continue;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst[e]), "r"(pack_bf16x2(f[e][0].x, f[e][0].y)),
+                           "r"(pack_bf16x2(f[e][0].z, f[e][0].w)), "r"(pack_bf16x2(f[e][1].x, f[e][1].y)),
+                           "r"(pack_bf16x2(f[e][1].z, f[e][1].w)) : "memory");
+            }
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(fb);
+          if (++stage == UG_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (IM2COL && warp != 1) {
       // ================= producer, im2col-free patch rows (warps 0, 2, 3: 96 threads) =================
       // Row r of the A tile is one token; its k-block kb is 128 bytes: rows dh0, dh0 + 1 (16 floats each) of the token's
       // 16 x 16 patch in (channel c, frame dt of the tubelet), kb = ((c * tub + dt) * 16 + dh0) / 2 -- exactly the
@@ -593,7 +678,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   } else {
     // ================= epilogue warpgroups (EW warps) =================
     // EW/4 warps per TMEM lane quarter, each taking BN/(EW/4) of the tile's columns, 32 columns at a time.
-    if constexpr (!IM2COL) reg_inc<EW == 8 ? 232 : 104>();   // pool: 640 x 96 at launch; 128 x (96 - 40) freed >= 512 x (104 - 96) claimed (112 would deadlock)
+    if constexpr (!GATHER) reg_inc<EW == 8 ? 232 : 104>();   // pool: 640 x 96 at launch; 128 x (96 - 40) freed >= 512 x (104 - 96) claimed (112 would deadlock)
     const int q = warp & 3;                          // TMEM lane quarter this warp may touch
     const int ew = warp - 4;
     const int part = ew >> 2;
@@ -1071,7 +1156,7 @@ int avj_gemm_umma(int layout, const void* A, const void* B, void* C, int M, int 
 // ------------------------------------------------------------------------------------------
 // Replaces the Conv3d / Conv2d projections of the reference (src/models/utils/patch_embed.py:85-102) for the tokens a
 // mask keeps (or all of them): no [tokens, kd] patch matrix is ever materialised, the producer warps of
-// gemm_umma_kernel<EPI_TRANSPOSED, 8, false, true> gather patch rows straight out of the clip into the operand tile.
+// gemm_umma_kernel<EPI_TRANSPOSED, 8, false, 1> gather patch rows straight out of the clip into the operand tile.
 static int get_tensor_map_f32_2d(const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer,
                                  CUtensorMap* out) {
   PFN_encodeTiled enc = get_encode_fn();
@@ -1117,7 +1202,7 @@ int avj_patch_embed_umma(const float* x, const int64_t* idx, const float* w, flo
   int rc = get_tensor_map_f32_2d(w, (uint64_t)kd, (uint64_t)D, (uint64_t)kd, 32, (uint32_t)p.block_n, &mb);
   if (rc) return rc;
 
-  auto kern = gemm_umma_kernel<EPI_TRANSPOSED, 8, false, true>;
+  auto kern = gemm_umma_kernel<EPI_TRANSPOSED, 8, false, 1>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, UG_SMEM_BYTES); });
@@ -1125,6 +1210,56 @@ int avj_patch_embed_umma(const float* x, const int64_t* idx, const float* w, flo
   const int units = p.tiles_m * p.tiles_n;
   const int sms = avj_num_sms();
   avj_launch_pdl(kern, dim3(units < sms ? units : sms), dim3(128 + 32 * 8), UG_SMEM_BYTES, s, ma, mb, mc, mp, p);
+  AVJ_LAUNCH_CHECK();
+  return 0;
+}
+
+// Weight gradient of the patch embedding without a patch matrix: gw[D, kd] += dy^T[D, tokens] . patches[tokens, kd], the
+// second operand gathered (and converted to bf16) out of the clip by the producer warps of
+// gemm_umma_kernel<EPI_TRANSPOSED, 8, false, 2>.  dy: bf16 [B * Kt, D] row-major.  Split along the tokens over CTAs like every
+// weight gradient (fp32 atomics into gw).
+int avj_patch_embed_wgrad_umma(const float* x, const int64_t* idx, const void* dy, float* gw, int B, int C, int T, int H, int W, int tub,
+                               int patch, int Kt, int D, cudaStream_t s) {
+  AVJ_CHECK(avj_patch_embed_umma_supported(patch, H, W, T, tub, D) && D % 8 == 0, "avj_patch_embed_wgrad: unsupported geometry");
+  AVJ_CHECK(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(gw)) & 15) == 0,
+            "avj_patch_embed_wgrad: x, dy and gw must be 16-byte aligned");
+  const int n_w = W / 16, n_h = H / 16, n_full = (T / tub) * n_h * n_w;
+  const int kd = C * tub * 256;
+  AVJ_CHECK(idx != nullptr || Kt == n_full, "avj_patch_embed_wgrad: without a token list every token contributes (Kt must be %d)", n_full);
+  AVJ_CHECK((int64_t)B * C * T * H * W < (int64_t)1 << 31, "avj_patch_embed_wgrad: input larger than 2^31 elements");
+  const int tokens = B * Kt;
+  if (tokens == 0) return 0;
+  UmmaParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = D; p.N = kd; p.K = tokens; p.ldc = kd; p.C = gw;
+  p.ep.accumulate = 1; p.ep.out_dtype = AVJ_F32;
+  p.k_blocks = (tokens + UG_BK - 1) / UG_BK;
+  p.a_mn_major = 1; p.b_mn_major = 1;
+  p.mn_lbo = env_u32("AVJ_UMMA_MN_LBO", 8192 / 16); p.mn_sbo = env_u32("AVJ_UMMA_MN_SBO", 1024 / 16); p.mn_kadv = env_u32("AVJ_UMMA_MN_KADV", 2048 / 16);
+  p.block_n = kd % 256 == 0 ? 256 : (kd % 128 == 0 ? 128 : 64);
+  p.tiles_m = (D + UG_BM - 1) / UG_BM;
+  p.tiles_n = kd / p.block_n;
+  const int sms = avj_num_sms();
+  const int tiles = p.tiles_m * p.tiles_n;
+  int split = sms / tiles;                                  // one wave of (tile, token range) units
+  if (split > p.k_blocks) split = p.k_blocks;
+  if (split < 1) split = 1;
+  p.kb_per_split = (p.k_blocks + split - 1) / split;
+  p.split_k = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;
+  p.ic_x = x; p.ic_idx = idx; p.ic_kt = Kt; p.ic_nw = n_w; p.ic_nh = n_h; p.ic_tub = tub; p.ic_c = C; p.ic_t = T;
+
+  CUtensorMap ma, mb, mc, mp;
+  memset(&mb, 0, sizeof(mb)); memset(&mc, 0, sizeof(mc)); memset(&mp, 0, sizeof(mp));
+  int rc = get_tensor_map(dy, (uint64_t)D, (uint64_t)tokens, (uint64_t)D, 64, UG_BK, &ma);
+  if (rc) return rc;
+  auto kern = gemm_umma_kernel<EPI_TRANSPOSED, 8, false, 2>;
+  const int smem = UG_SMEM_BYTES + 512;                     // + the token-offset tables of the gather
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
+  AVJ_CHECK(attr_err == cudaSuccess, "cudaFuncSetAttribute(patch-embed wgrad kernel) failed: %s", cudaGetErrorString(attr_err));
+  const int units = tiles * p.split_k;
+  avj_launch_pdl(kern, dim3(units < sms ? units : sms), dim3(128 + 32 * 8), (size_t)smem, s, ma, mb, mc, mp, p);
   AVJ_LAUNCH_CHECK();
   return 0;
 }

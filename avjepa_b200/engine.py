@@ -170,6 +170,12 @@ def patch_embed(x, idx, w_f32, out, B, Cin, T, H, W, tub, patch, K, D, ldc, bias
                int(D), int(ldc), C.byref(ep), stream())
 
 
+def patch_embed_wgrad(x, idx, dy_bf16, gw, B, Cin, T, H, W, tub, patch, K, D):
+    """Conv weight gradient of the patch projection, patch values gathered straight out of the clip (avj_patch_embed_wgrad)."""
+    _cabi.call('avj_patch_embed_wgrad', x, idx, dy_bf16, gw, int(B), int(Cin), int(T), int(H), int(W), int(tub), int(patch), int(K), int(D),
+               stream())
+
+
 def layernorm_fwd(x, gamma, beta, y, y_dtype, mean, rstd, rows, D, eps):
     _cabi.call('avj_layernorm_fwd', x, gamma, beta, y, y_dtype, mean, rstd, int(rows), int(D), float(eps), stream())
 

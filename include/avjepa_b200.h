@@ -102,6 +102,13 @@ int avj_patchify(const float* x, const int64_t* idx, void* out, int out_dtype,
 int avj_patch_embed(const float* x, const int64_t* idx, const float* w, float* out,
                     int B, int C, int T, int H, int W, int tub, int patch, int K, int D, int ldc,
                     const avj_epilogue* ep, void* stream);
+/* Weight gradient of the same projection, also without a patch matrix (autograd of patch_embed.py:85-102 w.r.t. the Conv weight):
+ *        gw[D, C*tub*256] += sum over b, j of dy[b*K + j, :]^T (x) patch(x[b], token idx[b, j])
+ *      dy bf16 [B*K, D] row-major (the gradient of the embedded rows, compute dtype), gw the fp32 gradient of the Conv weight
+ *      viewed [D, C*tub*16*16].  The patch values are gathered out of x and converted to bf16 by the producer warps of the
+ *      tcgen05 GEMM (MN-major operand tile); the token dimension is split over CTAs (fp32 atomics into gw). */
+int avj_patch_embed_wgrad(const float* x, const int64_t* idx, const void* dy, float* gw,
+                          int B, int C, int T, int H, int W, int tub, int patch, int K, int D, void* stream);
 /* 1 when avj_patch_embed accepts this geometry. */
 int avj_patch_embed_supported(int patch, int H, int W, int T, int tub, int D);
 

@@ -245,6 +245,32 @@ def check_patch_embed(B=3, D=192, seed=0, audio=False, masked=True):
     return (e < 2e-3 and untouched), e
 
 
+def check_patch_embed_wgrad(B=3, D=192, seed=0, audio=False, masked=True):
+    """avj_patch_embed_wgrad (patch values gathered by the GEMM producer, bf16 tensor cores, fp32 accumulate INTO gw) against
+    the autograd weight gradient of Conv3d in fp64."""
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    if audio:
+        x = torch.randn((B, 1, 1, 128, 192), generator=g, device=DEV)
+        Cc, T, H, W, tub, ntok = 1, 1, 128, 192, 1, 96
+    else:
+        x = torch.randn((B, 3, 16, 224, 224), generator=g, device=DEV)
+        Cc, T, H, W, tub, ntok = 3, 16, 224, 224, 2, 1568
+    kd = Cc * tub * 256
+    K = 77 if masked else ntok
+    idx = torch.stack([torch.randperm(ntok, generator=g, device=DEV)[:K].sort().values for _ in range(B)]) if masked else None
+    dy = (torch.randn((B * K, D), generator=g, device=DEV) * 0.3).to(torch.bfloat16)
+    gw0 = torch.randn((D, kd), generator=g, device=DEV)
+    gw = gw0.clone()
+    engine.patch_embed_wgrad(x.data_ptr(), idx.data_ptr() if masked else None, dy.data_ptr(), gw.data_ptr(), B, Cc, T, H, W, tub, 16, K, D)
+    w = torch.zeros((D, Cc, tub, 16, 16), dtype=torch.float64, device=DEV, requires_grad=True)
+    conv = torch.nn.functional.conv3d(x.to(torch.bfloat16).double(), w, stride=(tub, 16, 16)).flatten(2).transpose(1, 2)     # [B, ntok, D]
+    sel = torch.gather(conv, 1, idx.unsqueeze(-1).repeat(1, 1, D)) if masked else conv
+    (sel.reshape(B * K, D) * dy.double()).sum().backward()
+    ref = gw0.double() + w.grad.reshape(D, kd)
+    e = _rel(gw - gw0, ref - gw0.double())
+    return e < 2e-3, e
+
+
 def check_rows(seed=0):
     """copy_rows / colsum / fill_mask_tokens with non-trivial row maps."""
     g = torch.Generator(device=DEV).manual_seed(seed)

@@ -114,6 +114,14 @@ def test_patch_embed_im2col_free(audio, masked, D):
     assert ok, f'rel err {err}'
 
 
+@pytest.mark.parametrize('audio,masked,D', [(False, True, 192), (False, False, 128), (True, True, 384), (True, False, 64),
+                                            (False, True, 1024)])
+def test_patch_embed_weight_gradient_without_patch_matrix(audio, masked, D):
+    import kernel_checks as kc
+    ok, err = kc.check_patch_embed_wgrad(D=D, audio=audio, masked=masked)
+    assert ok, f'rel err {err}'
+
+
 def test_row_kernels():
     import kernel_checks as kc
     ok, err = kc.check_rows()

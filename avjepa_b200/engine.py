@@ -17,6 +17,7 @@ Residual stream and its gradient are fp32; GEMM/attention operands are the compu
 """
 import ctypes as C
 import os
+import threading
 
 import torch
 
@@ -67,24 +68,27 @@ class _BufferPool(object):
 
     def __init__(self):
         self.free = {}
+        self.lock = threading.RLock()      # arenas die on the autograd thread while the main thread builds the next ones
 
     def take(self, nbytes, device):
         key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-        lst = self.free.setdefault(key, [])
-        best = None
-        for i, b in enumerate(lst):
-            if nbytes <= b.numel() <= 2 * nbytes and (best is None or b.numel() < lst[best].numel()):
-                best = i
-        if best is not None:
-            return key, lst.pop(best)
+        with self.lock:
+            lst = self.free.setdefault(key, [])
+            best = None
+            for i, b in enumerate(lst):
+                if nbytes <= b.numel() <= 2 * nbytes and (best is None or b.numel() < lst[best].numel()):
+                    best = i
+            if best is not None:
+                return key, lst.pop(best)
         return key, torch.empty(int(nbytes * 1.12) + (1 << 20), dtype=torch.uint8, device=device)
 
     def give(self, key, buf):
-        lst = self.free.setdefault(key, [])
-        lst.append(buf)
-        if len(lst) > 8:                                   # keep the largest ones
-            lst.sort(key=lambda b: b.numel())
-            del lst[0]
+        with self.lock:
+            lst = self.free.setdefault(key, [])
+            lst.append(buf)
+            if len(lst) > 8:                               # keep the largest ones
+                lst.sort(key=lambda b: b.numel())
+                del lst[0]
 
 
 _POOL = _BufferPool()

@@ -1,5 +1,6 @@
-// K7 flash-attention BACKWARD on the 5th-gen tensor cores (sm_100a), two deterministic passes built
-// from ONE kernel template (no atomics, no dQ accumulation buffer):
+// K7 flash-attention BACKWARD on the 5th-gen tensor cores (sm_100a).  ONE kernel template gives the two deterministic passes
+// below (head_dim 64 .. 128: no atomics, no dQ accumulation buffer) and, for head_dim <= 32, the SINGLE-PASS form in which
+// the KV pass also produces dQ (fp32 accumulator + TMA reduce-add, see SP further down):
 //
 //   KV pass (KV = true ): CTA owns 128 keys of one (batch, head) and streams 64-query tiles
 //        S^T  = K Q^T          P^T  = exp2(S^T * scale*log2e - lse*log2e)      (TMEM lane = key)

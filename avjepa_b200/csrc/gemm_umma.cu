@@ -1,11 +1,12 @@
 // K6 production GEMM for sm_100a: persistent, warp-specialised, TMA -> shared memory ->
 // tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> tcgen05.ld -> fused epilogue -> global.
 //
-//   warp 0      : TMA producer (one elected lane), 4-stage mbarrier ring
-//   warp 1      : TMEM allocator + MMA issuer (one elected lane), UMMA 128 x BN x 16
-//   warps 2..5  : epilogue; warp w owns TMEM lanes [32*(w%4), +32)
+//   warp 0      : TMA producer (one elected lane), mbarrier ring (4 stages; 6 in the CTA-pair kernel)
+//   warp 1      : TMEM allocator + MMA issuer (one elected lane), UMMA 128 x BN x 16 (256 x BN x 16 per CTA pair)
+//   warps 2, 3  : idle (they join the producer in the two gather variants of the patch embedding)
+//   warps 4..   : 8 or 16 epilogue warps; warp w owns TMEM lanes [32*(w%4), +32) and a share of the columns
 //
-// CTA tile 128 x BN x 64 with BN in {64,128,192,256} chosen to divide N.  Two TMEM accumulator
+// CTA tile 128 x BN x 64 (CTA pair: 256 x BN x 64) with BN in {64,128,192,256} chosen to divide N.  Two TMEM accumulator
 // buffers (2 x 256 columns) let the epilogue of tile i overlap the main loop of tile i+1.
 // Operand layouts: K-major (activations x weights^T, "NT"), MN-major B (dgrad, "NN") and
 // MN-major A and B (wgrad, "TN") -- the MN-major tiles are loaded as 64x64 TMA boxes and

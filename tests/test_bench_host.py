@@ -50,3 +50,16 @@ def test_roofline_block_from_a_recorded_step():
     # the step launches no patch-matrix kernel (family 7 'other', d0 == 1) any more: im2col-free in both directions
     with open(DUMP) as f:
         assert not any(int(r['family']) == 7 and int(r['d0']) == 1 for r in csv.DictReader(f))
+
+
+def test_step_flops_reproduce_the_surveys_figures():
+    """F_step = F_target + 3 F_ctx - 2 PE + 3 F_pred at the mean mask lengths of the vitl16 mask config gives
+    0.552 / 0.692 / 1.180 / 2.806 / 5.165 TFLOP per clip for ViT-T/S/B/L/H.  bench.py recomputes it from the actual lengths of
+    every timed step with the same function; this pins the function to the survey's numbers."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    lens = [(366, 9, 748, 59), (111, 48, 1096, 26)]        # (Kc_v, Kc_a, Kt_v, Kt_a) of mask 0 and mask 1
+    for model, want in (('vit_tiny', 0.552), ('vit_small', 0.692), ('vit_base', 1.180), ('vit_large', 2.806), ('vit_huge', 5.165)):
+        got = bench.step_flops(model, lens) / 1e12
+        assert abs(got / want - 1.0) < 2e-3, (model, got, want)

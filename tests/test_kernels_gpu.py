@@ -85,7 +85,8 @@ def test_layernorm(code, rows, D, affine):
                                           (BF16, 2, 375, 3, 64), (BF16, 1, 64, 1, 64), (BF16, 3, 159, 2, 64),
                                           (BF16, 1, 300, 2, 32), (BF16, 1, 200, 2, 16), (BF16, 1, 100, 2, 48),
                                           (BF16, 1, 129, 1, 8), (BF16, 2, 333, 3, 80), (BF16, 1, 260, 2, 96),
-                                          (BF16, 1, 200, 2, 112), (BF16, 1, 513, 2, 128)])
+                                          (BF16, 1, 200, 2, 112), (BF16, 1, 513, 2, 128),
+                                          (BF16, 1, 50, 2, 24), (BF16, 2, 100, 2, 32), (BF16, 1, 64, 3, 16)])
 def test_attention(code, B, N, H, hd):
     import kernel_checks as kc
     ok, err = kc.check_attention(code, B, N, H, hd)

@@ -59,7 +59,9 @@ class DeviceAVMaskCollator(object):
         self.device = torch.device(device)
         self.sync_host_rng = sync_host_rng
         # prefetch: the masks of the NEXT call are sampled on a side stream as soon as this call returns, so the one
-        # device->host read (the counts) never waits behind the training step's kernels
+        # device->host read (the counts) never waits behind the training step's kernels.  The look-ahead assumes the next
+        # call asks for the same batch size; if it does not, the prefetched draw is discarded (its random numbers are
+        # consumed), so the mask sequence then differs from the host collator's from that call on.
         self.prefetch = prefetch
         if prefetch and sync_host_rng:
             raise ValueError('prefetch keeps the device generator one call ahead; it cannot be mirrored into the host generator')
